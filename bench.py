@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""bench.py -- path-segments/s and ms/frame of the hot path on N B200s of one node.
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): the RTOW
+book-1 random-spheres scene, every sphere an instance of a tessellated unit sphere with
+the reference's subdivision mix 9/6/3/8/6/3 (optx/rtwo.cxx:138-234: ~8.8 M instanced
+triangles), 1200x800, 500 spp, depth 50, defocus blur on.  One "step" = one frame.
+
+  value      whole-job path-segments/s: segments of a frame / device time of a frame, scene
+             resident in HBM; at N>1 the frame's samples are split over the ranks (strong
+             scaling) and the fixed-point accumulation buffers are summed by one NCCL reduce
+             inside the timed region.
+  e2e        the same through the C ABI a host program calls per frame (rtx_render* +
+             rtx_postproc + rtx_read of the 8-bit image into host memory).
+  roofline   dominant kernel k_render: algorithmic bytes per segment of SURVEY.md 8(d)
+             (64*ceil(log2 N) + 48 + 128) x segments per launch / its CUDA-event duration.
+  cpu_baseline  the oracle's double-precision port of rtow.cxx (the reference's CPU path:
+             analytic spheres, exhaustive scan) on a bounded sample, all host threads.
+
+`--impl reference` times that CPU implementation alone, on the same image and scene.
+"""
+import argparse
+import ctypes
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "path-segments/s"
+UNIT = "segments/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--width", type=int, default=1200)
+    ap.add_argument("--height", type=int, default=800)
+    ap.add_argument("--spp", type=int, default=500)
+    ap.add_argument("--depth", type=int, default=50)
+    ap.add_argument("--mode", default="mesh", choices=["mesh", "analytic"])
+    ap.add_argument("--ndiv", type=int, default=None, help="one subdivision count for every sphere (default: reference mix)")
+    ap.add_argument("--seed", type=int, default=4711)
+    ap.add_argument("--cpu-spp", type=int, default=2, help="samples per pixel of the CPU baseline sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    geo = "analytic spheres" if a.mode == "analytic" else ("tessellated ndiv %d" % a.ndiv if a.ndiv is not None else "tessellated 9/6/3/8/6/3")
+    return "RTOW book-1 random spheres, %s, %dx%d, %d spp, depth %d, defocus on" % (geo, a.width, a.height, a.spp, a.depth)
+
+
+# ------------------------------------------------------------------------- CPU legs
+def cpu_leg(a, spp, steps=1, warmup=0):
+    """The reference's CPU path (oracle<double> port of rtow.cxx, analytic spheres, exhaustive
+    scan) on `spp` samples per pixel of the same image; returns (segments/s, cores, description)."""
+    import oracle as orc
+    from rtxplay_b200 import scenes
+    spheres = scenes.book1(seed=1)
+    tab, _ = scenes.table(spheres, "analytic")
+    cam = orc.camera_f32((13, 2, 3), (0, 0, 0), (0, 1, 0), 20., a.width / a.height, .1, 10.)
+    cores = os.cpu_count() or 1
+    times, segs = [], 0
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = orc.render(orc.F64_PCG, tab, cam, a.width, a.height, spp, a.depth, seed=a.seed, sample0=it * spp, threads=cores)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+            segs += int(out["rpp"].sum())
+    total = sum(times)
+    desc = "%dx%d, %d of %d spp per step, analytic spheres (rtow.cxx geometry), exhaustive scan, %d threads" % (
+        a.width, a.height, spp, a.spp, cores)
+    return segs / total, cores, desc, 1e3 * total / max(steps, 1)
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    val, cores, desc, ms = cpu_leg(a, a.cpu_spp, steps=max(a.steps, 1), warmup=min(a.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(a), "step": "bounded sample: " + desc},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = [int(r[0]) for r in self.rows if r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------- GPU leg
+class _DevArr:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 2}
+
+
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    from rtxplay_b200 import api, scenes
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    # scene + acceleration structures (outside the timed window, like optx/rtwo.cxx:133-250)
+    ctx = api.Context(local)
+    spheres = scenes.book1(seed=1)
+    scenes.load(ctx, spheres, a.mode, a.ndiv)
+    ctx.resize(a.width, a.height)
+    cam = api.camera(aspratio=a.width / a.height)
+    st0 = ctx.stats()
+    n_prims = st0["n_triangles_instanced"] if a.mode == "mesh" else st0["n_things"]
+
+    # this rank's share of the frame's samples: global indices rank, rank+world, ...
+    spp_local = a.spp // world + (1 if rank < a.spp % world else 0)
+    ptr, nbytes = ctx.device_ptr(api.BUF_ACCUM)
+    accum = torch.as_tensor(_DevArr(ptr, nbytes // 8), device=torch.device("cuda", local))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    image_host = torch.empty((a.height, a.width, 4), dtype=torch.uint8).pin_memory()
+    L, c = ctx._L, ctx._c
+
+    def frame(e2e):
+        p = ctx.params(cam, spp_local, a.depth, seed=a.seed, sample0=rank, sample_stride=world)
+        if world == 1 and not e2e:
+            ctx.render(p)                       # k_render + k_resolve
+            return
+        ctx.render_accumulate(p)
+        if world > 1:
+            dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
+            torch.cuda.current_stream().synchronize()
+        if rank == 0:
+            ctx.resolve(a.spp)
+            if e2e:
+                ctx.postproc(api.PP_SRGB)
+                ctx._ck(L.rtx_read(c, ctypes.c_int(api.BUF_IMAGE), ctypes.c_void_p(image_host.data_ptr()), ctypes.c_size_t(image_host.numel())))
+
+    def timed(steps, e2e):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev0.record()
+        t0 = time.perf_counter()
+        kern_ms = 0.0
+        for _ in range(steps):
+            flush.fill_(1)                      # L2 flush: 256 MiB write, larger than the 126 MB L2
+            frame(e2e)
+            kern_ms += ctx.last_render_ms()
+        ev1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        wall = time.perf_counter() - t0
+        ms = ev0.elapsed_time(ev1)
+        t = torch.tensor([ms, wall * 1e3, kern_ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.tolist()
+
+    for _ in range(max(a.warmup, 0)):
+        flush.fill_(1)
+        frame(False)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = ctx.stats()["launches"]
+    ms_dev, ms_wall, kern_ms = timed(a.steps, False)
+    st = ctx.stats()
+    launches = st["launches"] - launches0 - 1          # minus the k_sum_segments of the stats() call itself
+    segs_local = st["segments"] if world == 1 else None
+    # segments of the whole frame: after the reduce rank 0 holds the summed counters
+    seg_t = torch.tensor([st["segments"]], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.broadcast(seg_t, src=0)
+    segments = int(seg_t.item())
+    e2e_dev, e2e_wall, _ = timed(a.steps, True)
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+
+    if rank == 0:
+        ms_step = ms_dev / a.steps
+        value = segments / (ms_step * 1e-3)
+        e2e_ms = max(e2e_dev, e2e_wall) / a.steps
+        # roofline of k_render: per segment 64*D + B_prim + 128 bytes, 46*D + P + 60 flop
+        D = max(1, math.ceil(math.log2(max(n_prims, 2))))
+        b_prim, p_flop = (48, 56) if a.mode == "mesh" else (16, 29)
+        bytes_seg, flop_seg = 64 * D + b_prim + 128, 46 * D + p_flop + 60
+        k_ms = kern_ms / a.steps
+        segs_launch = segments / world                   # each rank's launch traces its share
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        achieved = segs_launch * bytes_seg / (k_ms * 1e-3) / 1e9
+        clocks = sampler.summary() if sampler else {}
+        sm_mhz = clocks.get("sm_mhz") or 1965
+        fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "segments_per_frame": segments, "paths_per_frame": a.width * a.height * a.spp,
+                       "things": st["n_things"], "triangles_instanced": st["n_triangles_instanced"], "triangles_stored": st["n_triangles"],
+                       "parallelism": "spp split over %d rank(s) + NCCL reduce of the u64 accumulation buffer" % world if world > 1 else "1 GPU",
+                       "l2": "256 MiB device write between steps (inside the timed region)",
+                       "ms_per_frame": ms_step, "ms_per_frame_e2e": e2e_ms, "wall_ms_per_step": ms_wall / a.steps},
+            "roofline": {"bound": "hbm", "kernel": "k_render", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "bytes_per_segment": bytes_seg, "kernel_ms": k_ms,
+                         "note": "algorithmic node+primitive bytes of SURVEY.md 8(d); the working set is L1/L2 resident, so this is a cache-bandwidth figure quoted against HBM peak",
+                         "fp32": {"flop_per_segment": flop_seg, "achieved_tflops": segs_launch * flop_seg / (k_ms * 1e-3) / 1e12,
+                                  "peak_tflops": fp32_peak, "frac": segs_launch * flop_seg / (k_ms * 1e-3) / 1e12 / fp32_peak}},
+            "e2e": {"value": segments / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": ctypes.sizeof(ctx.params(cam, 1)),
+                    "d2h_bytes_per_step": int(image_host.numel()), "ms_per_frame": e2e_ms},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if not a.no_cpu and world == 1:
+            v, cores, desc, _ = cpu_leg(a, a.cpu_spp)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

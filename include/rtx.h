@@ -1,0 +1,151 @@
+/* rtx.h -- C ABI of librtx.so, the B200-native replacement of RTXplay/RTWO's
+ * OptiX hot path.  Plain pointers and sizes only; every call is synchronous w.r.t. the
+ * host on return (the reference blocks in Launcher::ignite, optx/launcher.cxx:70).
+ *
+ * Each entry point names the reference interface it stands in for (file:line under
+ * /root/reference).  The C++ shims in rtxplay_b200/host/ (Scene, Launcher, pp_sRGB ...)
+ * sit on top of this header and keep the reference's class API source-compatible;
+ * INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Conventions: 0 = success, non-zero = failure with the text in rtx_last_error();
+ * the library owns all device memory; host pointers passed in are copied before the
+ * call returns; one calling thread per context.  There is NO CPU fallback: without a
+ * CUDA device rtx_init fails.
+ */
+#ifndef RTX_H
+#define RTX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rtx_ctx rtx_ctx ;
+
+/* optx/thing.h:17-45 -- Optics { int type ; union { Diffuse, Reflect, Refract } } */
+enum { RTX_OPTICS_DIFFUSE = 0, RTX_OPTICS_REFLECT = 1, RTX_OPTICS_REFRACT = 2 } ;
+typedef struct {
+	int32_t type ;
+	float   albedo[3] ;  /* diffuse / reflect (wavefront Kd) */
+	float   fuzz ;       /* reflect */
+	float   index ;      /* refract (wavefront Ni) */
+} rtx_optics ;
+
+/* The derived camera of optx/camera.h:30-48 (eye, u, v, hvec, wvec, dvec, aperture):
+ * what LpGeneral carries by value to the device (optx/rtwo.h:37). */
+typedef struct {
+	float eye[3], u[3], v[3], hvec[3], wvec[3], dvec[3] ;
+	float aperture ;
+} rtx_camera ;
+
+/* optx/rtwo.h:26-52 LpGeneral minus device pointers and the OptiX handle. */
+typedef struct {
+	uint32_t   image_w, image_h ;
+	uint32_t   spp ;            /* samples THIS call renders per pixel */
+	uint32_t   depth ;          /* max scatter events per path (rtow.cxx:99) */
+	rtx_camera camera ;
+	uint64_t   seed ;           /* stream key; the reference's constant is 4711 (optx/frand48.h:19) */
+	uint32_t   sample0 ;        /* global index of this call's first sample ... */
+	uint32_t   sample_stride ;  /* ... and the step between its samples (multi-GPU spp split) */
+	uint32_t   accumulate ;     /* 0: start from zero (optx/camera_i.cu:52); 1: add to the buffers */
+} rtx_params ;
+
+typedef struct {
+	uint64_t segments ;         /* closest-hit queries of the last render (sum of RPP, optx/rtwo.cxx:588) */
+	uint64_t paths ;
+	float    ms_render ;        /* device time of the path-tracing kernel(s) of the last rtx_render */
+	float    ms_build_blas ;    /* device time of all mesh LBVH builds so far */
+	float    ms_build_tlas ;    /* device time of the last top-level build or refit */
+	uint32_t launches ;         /* kernels launched by this context so far */
+	uint32_t n_things, n_meshes ;
+	uint64_t n_triangles ;      /* unique triangles stored */
+	uint64_t n_triangles_instanced ; /* sum over things of their mesh's triangles */
+	uint64_t bytes_device ;     /* device memory held */
+} rtx_stats ;
+
+/* buffers of rtx_read / rtx_device_ptr */
+enum {
+	RTX_BUF_ACCUM   = 0,  /* uint64[4*w*h]: fixed-point (2^-32) radiance sums r,g,b and segment count */
+	RTX_BUF_RAWRGB  = 1,  /* float[3*w*h]  LpGeneral.rawRGB  (optx/launcher.cxx:39) */
+	RTX_BUF_RPP     = 2,  /* uint32[w*h]   LpGeneral.rpp     (optx/launcher.cxx:41) */
+	RTX_BUF_IMAGE   = 3,  /* uint8[4*w*h]  LpGeneral.image   (optx/rtwo.cxx:564)   */
+	RTX_BUF_HIT_ID  = 4,  /* int64[w*h]    first-hit id of rtx_primary_hits: thing<<32 | prim+1, -1 = miss */
+	RTX_BUF_HIT_T   = 5,  /* float[w*h]    its ray parameter */
+	RTX_BUF_NORMALS = 6,  /* float[3*w*h]  LpGeneral.normals (optx/launcher.cxx:43) */
+	RTX_BUF_ALBEDOS = 7   /* float[3*w*h]  LpGeneral.albedos (optx/launcher.cxx:44) */
+} ;
+
+enum { RTX_PP_NONE = 0, RTX_PP_SRGB = 1 } ;
+
+/* cudaFree(0) + optixInit + optixDeviceContextCreate, optx/rtwo.cxx:115-128 */
+int  rtx_init( int device, rtx_ctx** out ) ;
+void rtx_shutdown( rtx_ctx* ctx ) ;
+/* util_cpu.h:18-53 CUDA_CHECK/OPTX_CHECK text; ctx may be NULL for rtx_init failures */
+const char* rtx_last_error( const rtx_ctx* ctx ) ;
+
+/* Scene::add( Object& ), optx/scene.cxx:38-167: upload float3 vertices + uint3 indices and
+ * build the mesh's bottom-level LBVH (replaces optixAccelBuild on a GAS). */
+int rtx_mesh_create( rtx_ctx* ctx, const float* xyz, uint32_t n_vertices, const uint32_t* idx, uint32_t n_triangles, uint32_t* mesh_id ) ;
+/* The analytic unit sphere of the CPU path (sphere.h:20-48) as a pseudo mesh: a thing
+ * instancing it is the sphere centre = translation, radius = transform[0]. */
+int rtx_sphere_create( rtx_ctx* ctx, uint32_t* mesh_id ) ;
+/* Scene::add( Thing&, unsigned object ), optx/scene.cxx:169-196 (identity transform) */
+int rtx_thing_add( rtx_ctx* ctx, uint32_t mesh_id, const rtx_optics* optics, uint32_t* thing_id ) ;
+/* Scene::set / Scene::get, optx/scene.cxx:198-225: row-major 3x4 object->world */
+int rtx_thing_set_xf( rtx_ctx* ctx, uint32_t thing_id, const float xf[12] ) ;
+int rtx_thing_get_xf( rtx_ctx* ctx, uint32_t thing_id, float xf[12] ) ;
+int rtx_thing_set_optics( rtx_ctx* ctx, uint32_t thing_id, const rtx_optics* optics ) ;
+/* Scene::build, optx/scene.cxx:227-273 (IAS build) and Scene::update, :275-294 (IAS refit) */
+int rtx_accel_build( rtx_ctx* ctx ) ;
+int rtx_accel_refit( rtx_ctx* ctx ) ;
+
+/* Launcher::resize, optx/launcher.cxx:36-47 */
+int rtx_resize( rtx_ctx* ctx, uint32_t w, uint32_t h ) ;
+/* Launcher::ignite, optx/launcher.cxx:49-77 + __raygen__camera's per-pixel mean/clamp
+ * (optx/camera_i.cu:105): path-trace p->spp samples per pixel into the accumulation
+ * buffer and resolve rawRGB / rpp.  Blocking. */
+int rtx_render( rtx_ctx* ctx, const rtx_params* p ) ;
+/* The same without the resolve: used when partial sums of several GPUs are reduced first. */
+int rtx_render_accumulate( rtx_ctx* ctx, const rtx_params* p ) ;
+/* mean -> clamp(0,1) -> rawRGB, rpp; total_spp = samples summed into the buffer */
+int rtx_resolve( rtx_ctx* ctx, uint64_t total_spp ) ;
+/* Launcher::ignite( stream, once=true ) + picker (optx/camera_i.cu:27-29, optx/simplesm.cxx:1014-1034):
+ * one primary ray through the pixel; UINT32_MAX = miss */
+int rtx_pick( rtx_ctx* ctx, const rtx_params* p, uint32_t x, uint32_t y, uint32_t* thing_id ) ;
+/* pp_none / pp_sRGB, optx/postproc.cu:49-61: rawRGB -> uchar4 image buffer */
+int rtx_postproc( rtx_ctx* ctx, int kind ) ;
+/* the same on caller-owned DEVICE buffers, for callers that keep the reference signature */
+int rtx_postproc_dev( rtx_ctx* ctx, int kind, const void* src_float3_dev, void* dst_uchar4_dev, int w, int h ) ;
+
+/* parity instruments: first hit of the primary rays of one sample, and closest hits of
+ * caller-supplied rays through the LBVH (brute=0) or by exhaustive scan on the GPU (brute=1) */
+int rtx_primary_hits( rtx_ctx* ctx, const rtx_params* p ) ;
+int rtx_trace_rays( rtx_ctx* ctx, uint32_t n, const float* ori_xyz, const float* dir_xyz, float tmin, int brute, int64_t* id_out, float* t_out ) ;
+
+/* imgtopnm's device->host copy, optx/rtwo.cxx:61-74 */
+int rtx_read( rtx_ctx* ctx, int buffer, void* host_dst, size_t bytes ) ;
+/* device address of a buffer (e.g. to hand the accumulation buffer to NCCL) */
+int rtx_device_ptr( rtx_ctx* ctx, int buffer, void** dev_ptr, size_t* bytes ) ;
+/* overwrite a buffer from host memory (tests; loading reduced sums back) */
+int rtx_write( rtx_ctx* ctx, int buffer, const void* host_src, size_t bytes ) ;
+
+/* the -S line of optx/rtwo.cxx:579-591 and more */
+int rtx_stats_get( rtx_ctx* ctx, rtx_stats* out ) ;
+/* device time (CUDA events on the launching stream) of the path-tracing kernel of the last
+ * rtx_render / rtx_render_accumulate -- the window optx/rtwo.cxx:542-546 times; no device work */
+int rtx_last_render_ms( rtx_ctx* ctx, float* ms ) ;
+
+/* host helpers shared by the C++ shims and the tests (no device work) */
+/* Camera::set, optx/camera.h:30-48 */
+void rtx_camera_set( rtx_camera* cam, const float eye[3], const float pat[3], const float vup[3], float fov, float aspratio, float aperture, float fostance ) ;
+/* Sphere tessellation by subdivided tetrahedron, optx/sphere.cxx:28-106.  Call with
+ * xyz = idx = NULL to get the counts (2*4^n+2 vertices, 4*4^n triangles). */
+int rtx_sphere_mesh( float radius, uint32_t ndiv, float* xyz, uint32_t* n_vertices, uint32_t* idx, uint32_t* n_triangles ) ;
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* RTX_H */

@@ -319,14 +319,14 @@ template <class R, class Rng> struct Tracer {
 		const R inv = R( 1 )/det ;
 		const V3<R> s = ( ohi-T.v0 )+olo ;
 		u = dot( s, p )*inv ;
-		if ( u<R( 0 ) || u>R( 1 ) )
+		if ( ! ( u>=R( 0 ) && u<=R( 1 ) ) )       // written so that a NaN rejects
 			return false ;
 		const V3<R> q = cross( s, T.e1 ) ;
 		v = dot( d, q )*inv ;
-		if ( v<R( 0 ) || u+v>R( 1 ) )
+		if ( ! ( v>=R( 0 ) && u+v<=R( 1 ) ) )
 			return false ;
 		t = dot( T.e2, q )*inv ;
-		if ( tmin>t || t>tmax )
+		if ( ! ( t>=tmin && t<=tmax ) )
 			return false ;
 		return true ;
 	}

@@ -1,0 +1,645 @@
+// rtx_api.cu -- the C ABI of include/rtx.h: context, geometry upload, LBVH builds,
+// frame buffers and kernel launches.  One translation unit, compiled for sm_100a with
+// -fmad=false (see rtx_core.cuh for why).  There is no CPU path in here: every entry
+// point that computes launches CUDA kernels, and rtx_init fails without a device.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/rtx.h"
+#include "rtx_core.cuh"
+#include "rtx_lbvh.cuh"
+#include "rtx_kernels.cuh"
+#include "rtx_hostmath.h"
+
+using namespace rtx ;
+
+static_assert( sizeof( ThingTrav ) == 128, "ThingTrav layout" ) ;
+static_assert( sizeof( ThingShade ) == 144, "ThingShade layout" ) ;
+static_assert( sizeof( q4 ) == 16, "q4 layout" ) ;
+
+namespace {
+
+thread_local std::string g_init_error ;
+
+#define CK( call ) do { cudaError_t e_ = ( call ) ; if ( e_ != cudaSuccess ) { \
+	char b_[512] ; snprintf( b_, sizeof( b_ ), "CUDA call (%s) failed with error '%s' (%s:%d)", #call, cudaGetErrorString( e_ ), __FILE__, __LINE__ ) ; \
+	throw std::runtime_error( b_ ) ; } } while ( 0 )
+
+struct Lbvh {           // one built tree and, when kept, what a refit needs
+	uint32_t  n = 0 ;
+	q4*       nodes = nullptr ;
+	uint32_t* order = nullptr ;   // leaf slot -> primitive
+	int2*     child = nullptr ;
+	int*      parent_inner = nullptr ;
+	int*      parent_leaf = nullptr ;
+	q4*       blo = nullptr ;
+	q4*       bhi = nullptr ;
+	uint32_t* flags = nullptr ;
+	q4        root_lo = { 0, 0, 0, 0 }, root_hi = { 0, 0, 0, 0 } ;
+} ;
+
+struct Mesh {
+	bool      analytic = false ;
+	uint32_t  nv = 0, nt = 0 ;
+	float*    vces = nullptr ;
+	uint32_t* ices = nullptr ;
+	q4*       tris = nullptr ;
+	Lbvh      bvh ;
+} ;
+
+struct ThingHost {
+	uint32_t   mesh ;
+	rtx_optics optics ;
+	float      xf[12] ;
+} ;
+
+} // namespace
+
+struct rtx_ctx {
+	int          device = 0 ;
+	std::string  err ;
+	cudaStream_t stream = nullptr ;
+	cudaEvent_t  ev0 = nullptr, ev1 = nullptr ;
+
+	std::vector<Mesh>      meshes ;
+	std::vector<ThingHost> things ;
+
+	// device scene
+	ThingTrav*  d_trav = nullptr ;
+	ThingShade* d_shade = nullptr ;
+	q4*         d_tb_lo = nullptr ;   // per-thing mesh root boxes, then world boxes
+	q4*         d_tb_hi = nullptr ;
+	q4*         d_tp_lo = nullptr ;
+	q4*         d_tp_hi = nullptr ;
+	uint32_t    n_things_dev = 0 ;
+	Lbvh        tlas ;
+	bool        built = false ;
+
+	// frame
+	uint32_t  w = 0, h = 0 ;
+	uint64_t* d_accum = nullptr ;
+	float*    d_raw = nullptr ;
+	uint32_t* d_rpp = nullptr ;
+	uchar4*   d_image = nullptr ;
+	int64_t*  d_hit_id = nullptr ;
+	float*    d_hit_t = nullptr ;
+	float*    d_normals = nullptr ;
+	float*    d_albedos = nullptr ;
+	uint32_t* d_pick = nullptr ;
+	unsigned long long* d_counter = nullptr ;
+
+	// statistics
+	uint64_t bytes = 0 ;
+	uint32_t launches = 0 ;
+	float    ms_render = 0.f, ms_blas = 0.f, ms_tlas = 0.f ;
+	uint64_t paths = 0 ;
+} ;
+
+namespace {
+
+template <class T> T* dalloc( rtx_ctx* c, size_t n ) {
+	T* p = nullptr ;
+	if ( n == 0 ) n = 1 ;
+	CK( cudaMalloc( reinterpret_cast<void**>( &p ), n*sizeof( T ) ) ) ;
+	c->bytes += n*sizeof( T ) ;
+	return p ;
+}
+template <class T> void dfree( rtx_ctx* c, T*& p, size_t n ) {
+	if ( p ) { cudaFree( p ) ; c->bytes -= ( n ? n : 1 )*sizeof( T ) ; p = nullptr ; }
+}
+
+void lbvh_free( rtx_ctx* c, Lbvh& b ) {
+	const size_t n = b.n ;
+	dfree( c, b.nodes, ( n>1 ? n-1 : 1 )*RTX_NODE_RECS ) ;
+	dfree( c, b.order, n ) ;
+	dfree( c, b.child, n>1 ? n-1 : 1 ) ;
+	dfree( c, b.parent_inner, n>1 ? n-1 : 1 ) ;
+	dfree( c, b.parent_leaf, n ) ;
+	dfree( c, b.blo, 2*n ) ;
+	dfree( c, b.bhi, 2*n ) ;
+	dfree( c, b.flags, n>1 ? n-1 : 1 ) ;
+	b.n = 0 ;
+}
+
+// bottom-up boxes + traversal nodes for an existing topology
+void lbvh_refit( rtx_ctx* c, Lbvh& b, const q4* plo, const q4* phi ) {
+	const int n = int( b.n ) ;
+	CK( cudaMemsetAsync( b.flags, 0, sizeof( uint32_t )*( n>1 ? n-1 : 1 ), c->stream ) ) ;
+	k_refit<<<( n+255 )/256, 256, 0, c->stream>>>( plo, phi, b.order, n, b.child, b.parent_inner, b.parent_leaf, b.blo, b.bhi, b.flags ) ;
+	k_emit<<<( n+255 )/256, 256, 0, c->stream>>>( n, b.child, b.blo, b.bhi, b.nodes ) ;
+	c->launches += 2 ;
+	CK( cudaGetLastError() ) ;
+	CK( cudaMemcpyAsync( &b.root_lo, b.blo, sizeof( q4 ), cudaMemcpyDeviceToHost, c->stream ) ) ;
+	CK( cudaMemcpyAsync( &b.root_hi, b.bhi, sizeof( q4 ), cudaMemcpyDeviceToHost, c->stream ) ) ;
+	CK( cudaStreamSynchronize( c->stream ) ) ;
+}
+
+// Morton keys -> radix sort -> Karras hierarchy -> refit -> nodes
+void lbvh_build( rtx_ctx* c, Lbvh& b, const q4* plo, const q4* phi, uint32_t n ) {
+	lbvh_free( c, b ) ;
+	b.n = n ;
+	b.nodes        = dalloc<q4>( c, size_t( n>1 ? n-1 : 1 )*RTX_NODE_RECS ) ;
+	b.order        = dalloc<uint32_t>( c, n ) ;
+	b.child        = dalloc<int2>( c, n>1 ? n-1 : 1 ) ;
+	b.parent_inner = dalloc<int>( c, n>1 ? n-1 : 1 ) ;
+	b.parent_leaf  = dalloc<int>( c, n ) ;
+	b.blo          = dalloc<q4>( c, 2*size_t( n ) ) ;
+	b.bhi          = dalloc<q4>( c, 2*size_t( n ) ) ;
+	b.flags        = dalloc<uint32_t>( c, n>1 ? n-1 : 1 ) ;
+
+	const uint32_t nblocks = ( n+RTX_RS_TILE-1 )/RTX_RS_TILE ;
+	int* bounds = dalloc<int>( c, 6 ) ;
+	uint64_t* keys0 = dalloc<uint64_t>( c, n ) ; uint64_t* keys1 = dalloc<uint64_t>( c, n ) ;
+	uint32_t* vals1 = dalloc<uint32_t>( c, n ) ;
+	uint32_t* counts = dalloc<uint32_t>( c, size_t( 256 )*nblocks ) ;
+
+	k_bounds_init<<<1, 32, 0, c->stream>>>( bounds ) ;
+	k_bounds_reduce<<<min( 1184u, ( n+255u )/256u ), 256, 0, c->stream>>>( plo, phi, n, bounds ) ;
+	k_morton<<<( n+255 )/256, 256, 0, c->stream>>>( plo, phi, n, bounds, keys0, b.order ) ;
+	c->launches += 3 ;
+	uint64_t* kin = keys0 ; uint64_t* kout = keys1 ;
+	uint32_t* vin = b.order ; uint32_t* vout = vals1 ;
+	for ( int pass = 0 ; pass<8 ; pass++ ) {
+		const int shift = 8*pass ;
+		k_radix_hist<<<nblocks, 32, 0, c->stream>>>( kin, n, shift, counts, nblocks ) ;
+		k_radix_scan<<<1, 1024, 0, c->stream>>>( counts, 256u*nblocks ) ;
+		k_radix_scatter<<<nblocks, 32, 0, c->stream>>>( kin, vin, n, shift, counts, nblocks, kout, vout ) ;
+		c->launches += 3 ;
+		std::swap( kin, kout ) ; std::swap( vin, vout ) ;
+	}
+	// 8 passes: the sorted data is back in keys0 / b.order
+	if ( n>1 ) {
+		k_karras<<<( n-1+255 )/256, 256, 0, c->stream>>>( keys0, int( n ), b.child, b.parent_inner, b.parent_leaf ) ;
+		c->launches += 1 ;
+	}
+	CK( cudaGetLastError() ) ;
+	lbvh_refit( c, b, plo, phi ) ;
+
+	dfree( c, bounds, 6 ) ; dfree( c, keys0, n ) ; dfree( c, keys1, n ) ; dfree( c, vals1, n ) ; dfree( c, counts, size_t( 256 )*nblocks ) ;
+}
+
+// host thing list -> device records + world bounds
+void upload_things( rtx_ctx* c ) {
+	const uint32_t n = uint32_t( c->things.size() ) ;
+	if ( n != c->n_things_dev ) {
+		dfree( c, c->d_trav, c->n_things_dev ) ; dfree( c, c->d_shade, c->n_things_dev ) ;
+		dfree( c, c->d_tb_lo, c->n_things_dev ) ; dfree( c, c->d_tb_hi, c->n_things_dev ) ;
+		dfree( c, c->d_tp_lo, c->n_things_dev ) ; dfree( c, c->d_tp_hi, c->n_things_dev ) ;
+		c->d_trav = dalloc<ThingTrav>( c, n ) ; c->d_shade = dalloc<ThingShade>( c, n ) ;
+		c->d_tb_lo = dalloc<q4>( c, n ) ; c->d_tb_hi = dalloc<q4>( c, n ) ;
+		c->d_tp_lo = dalloc<q4>( c, n ) ; c->d_tp_hi = dalloc<q4>( c, n ) ;
+		c->n_things_dev = n ;
+	}
+	std::vector<ThingTrav> trav( n ) ; std::vector<ThingShade> shade( n ) ; std::vector<q4> lo( n ), hi( n ) ;
+	for ( uint32_t k = 0 ; k<n ; k++ ) {
+		const ThingHost& th = c->things[k] ;
+		const Mesh& m = c->meshes[th.mesh] ;
+		ThingTrav& t = trav[k] ; ThingShade& s = shade[k] ;
+		memset( &t, 0, sizeof( t ) ) ; memset( &s, 0, sizeof( s ) ) ;
+		for ( int j = 0 ; j<12 ; j++ ) s.xf[j] = double( th.xf[j] ) ;
+		s.albedo[0] = th.optics.albedo[0] ; s.albedo[1] = th.optics.albedo[1] ; s.albedo[2] = th.optics.albedo[2] ;
+		s.fuzz = th.optics.fuzz ; s.index = th.optics.index ; s.type = th.optics.type ;
+		if ( m.analytic ) {
+			t.kind = 0 ; s.kind = 0 ;
+			t.inv[0] = double( th.xf[3] ) ; t.inv[1] = double( th.xf[7] ) ; t.inv[2] = double( th.xf[11] ) ; t.inv[3] = double( th.xf[0] ) ;
+			lo[k] = { 0, 0, 0, 0 } ; hi[k] = { 0, 0, 0, 0 } ;
+		} else {
+			t.kind = 1 ; s.kind = 1 ;
+			affine_inverse( th.xf, t.inv ) ;
+			t.nodes = m.bvh.nodes ; t.tris = m.tris ; t.n_tris = m.nt ;
+			s.vces = m.vces ; s.ices = m.ices ;
+			lo[k] = m.bvh.root_lo ; hi[k] = m.bvh.root_hi ;
+		}
+	}
+	CK( cudaMemcpyAsync( c->d_trav, trav.data(), sizeof( ThingTrav )*n, cudaMemcpyHostToDevice, c->stream ) ) ;
+	CK( cudaMemcpyAsync( c->d_shade, shade.data(), sizeof( ThingShade )*n, cudaMemcpyHostToDevice, c->stream ) ) ;
+	CK( cudaMemcpyAsync( c->d_tb_lo, lo.data(), sizeof( q4 )*n, cudaMemcpyHostToDevice, c->stream ) ) ;
+	CK( cudaMemcpyAsync( c->d_tb_hi, hi.data(), sizeof( q4 )*n, cudaMemcpyHostToDevice, c->stream ) ) ;
+	CK( cudaStreamSynchronize( c->stream ) ) ;   // the host vectors go out of scope
+	if ( n ) {
+		k_thing_bounds<<<( n+127 )/128, 128, 0, c->stream>>>( c->d_trav, c->d_shade, c->d_tb_lo, c->d_tb_hi, n, c->d_tp_lo, c->d_tp_hi ) ;
+		c->launches += 1 ;
+		CK( cudaGetLastError() ) ;
+	}
+}
+
+SceneDev scene_dev( const rtx_ctx* c ) {
+	SceneDev S ;
+	S.tlas_nodes = c->tlas.nodes ; S.tlas_order = c->tlas.order ;
+	S.trav = c->d_trav ; S.shade = c->d_shade ; S.n_things = c->n_things_dev ;
+	return S ;
+}
+
+void free_frame( rtx_ctx* c ) {
+	const size_t np = size_t( c->w )*c->h ;
+	dfree( c, c->d_accum, 4*np ) ; dfree( c, c->d_raw, 3*np ) ; dfree( c, c->d_rpp, np ) ; dfree( c, c->d_image, np ) ;
+	dfree( c, c->d_hit_id, np ) ; dfree( c, c->d_hit_t, np ) ; dfree( c, c->d_normals, 3*np ) ; dfree( c, c->d_albedos, 3*np ) ;
+}
+
+CameraDev camera_dev( const rtx_camera& k ) {
+	CameraDev d ;
+	d.eye = mk3( k.eye[0], k.eye[1], k.eye[2] ) ; d.u = mk3( k.u[0], k.u[1], k.u[2] ) ; d.v = mk3( k.v[0], k.v[1], k.v[2] ) ;
+	d.hvec = mk3( k.hvec[0], k.hvec[1], k.hvec[2] ) ; d.wvec = mk3( k.wvec[0], k.wvec[1], k.wvec[2] ) ; d.dvec = mk3( k.dvec[0], k.dvec[1], k.dvec[2] ) ;
+	d.aperture = k.aperture ;
+	return d ;
+}
+
+FrameArgs frame_args( rtx_ctx* c, const rtx_params* p ) {
+	if ( ! c->built ) throw std::runtime_error( "rtx: acceleration structure not built (call rtx_accel_build)" ) ;
+	if ( p->image_w != c->w || p->image_h != c->h || c->w == 0 ) throw std::runtime_error( "rtx: image size differs from the last rtx_resize" ) ;
+	if ( p->image_w<2 || p->image_h<2 ) throw std::runtime_error( "rtx: image must be at least 2x2" ) ;
+	FrameArgs a ;
+	a.S = scene_dev( c ) ; a.cam = camera_dev( p->camera ) ;
+	a.w = p->image_w ; a.h = p->image_h ; a.spp = p->spp ; a.depth = p->depth ; a.seed = p->seed ;
+	a.sample0 = p->sample0 ; a.sample_stride = p->sample_stride ? p->sample_stride : 1u ; a.accumulate = p->accumulate ;
+	a.accum = c->d_accum ; a.hit_id = c->d_hit_id ; a.hit_t = c->d_hit_t ;
+	return a ;
+}
+
+void do_resolve( rtx_ctx* c, uint64_t total_spp ) {
+	const uint32_t np = c->w*c->h ;
+	k_resolve<<<( np+255 )/256, 256, 0, c->stream>>>( c->d_accum, np, total_spp ? total_spp : 1, c->d_raw, c->d_rpp ) ;
+	c->launches += 1 ;
+	CK( cudaGetLastError() ) ;
+}
+
+void do_render( rtx_ctx* c, const rtx_params* p, bool resolve ) {
+	const FrameArgs a = frame_args( c, p ) ;
+	CK( cudaEventRecord( c->ev0, c->stream ) ) ;
+	k_render<<<tile_grid( a.w, a.h ), RTX_BLOCK, 0, c->stream>>>( a ) ;
+	c->launches += 1 ;
+	CK( cudaGetLastError() ) ;
+	CK( cudaEventRecord( c->ev1, c->stream ) ) ;
+	if ( resolve )
+		do_resolve( c, p->spp ) ;
+	CK( cudaStreamSynchronize( c->stream ) ) ;
+	CK( cudaEventElapsedTime( &c->ms_render, c->ev0, c->ev1 ) ) ;
+	c->paths = uint64_t( a.w )*a.h*a.spp ;
+}
+
+struct BufInfo { void* ptr ; size_t bytes ; } ;
+BufInfo buffer_of( rtx_ctx* c, int buffer ) {
+	const size_t np = size_t( c->w )*c->h ;
+	switch ( buffer ) {
+		case RTX_BUF_ACCUM:   return { c->d_accum,   np*4*sizeof( uint64_t ) } ;
+		case RTX_BUF_RAWRGB:  return { c->d_raw,     np*3*sizeof( float ) } ;
+		case RTX_BUF_RPP:     return { c->d_rpp,     np*sizeof( uint32_t ) } ;
+		case RTX_BUF_IMAGE:   return { c->d_image,   np*4 } ;
+		case RTX_BUF_HIT_ID:  return { c->d_hit_id,  np*sizeof( int64_t ) } ;
+		case RTX_BUF_HIT_T:   return { c->d_hit_t,   np*sizeof( float ) } ;
+		case RTX_BUF_NORMALS: return { c->d_normals, np*3*sizeof( float ) } ;
+		case RTX_BUF_ALBEDOS: return { c->d_albedos, np*3*sizeof( float ) } ;
+	}
+	throw std::runtime_error( "rtx: unknown buffer id" ) ;
+}
+
+__global__ void __launch_bounds__( 256 ) k_sum_segments( const uint64_t* accum, uint32_t npix, unsigned long long* out ) {
+	unsigned long long s = 0 ;
+	for ( uint32_t p = blockIdx.x*blockDim.x+threadIdx.x ; p<npix ; p += gridDim.x*blockDim.x )
+		s += accum[4*size_t( p )+3] ;
+	for ( int o = 16 ; o>0 ; o >>= 1 )
+		s += __shfl_xor_sync( 0xffffffffu, s, o ) ;
+	if ( ( threadIdx.x&31 ) == 0 )
+		atomicAdd( out, s ) ;
+}
+
+} // namespace
+
+#define RTX_TRY( c ) try {
+#define RTX_END( c ) return 0 ; } catch ( const std::exception& e_ ) { if ( c ) ( c )->err = e_.what() ; else g_init_error = e_.what() ; cudaGetLastError() ; return 1 ; }
+
+extern "C" {
+
+int rtx_init( int device, rtx_ctx** out ) {
+	rtx_ctx* c = nullptr ;
+	try {
+		int n = 0 ;
+		if ( cudaGetDeviceCount( &n ) != cudaSuccess || n<1 )
+			throw std::runtime_error( "rtx_init: no CUDA device (this library has no CPU path)" ) ;
+		if ( device<0 || device>=n )
+			throw std::runtime_error( "rtx_init: device index out of range" ) ;
+		CK( cudaSetDevice( device ) ) ;
+		CK( cudaFree( 0 ) ) ;
+		cudaDeviceProp prop ;
+		CK( cudaGetDeviceProperties( &prop, device ) ) ;
+		if ( prop.major<10 )
+			throw std::runtime_error( "rtx_init: needs an sm_100a (Blackwell B200) device" ) ;
+		c = new rtx_ctx ;
+		c->device = device ;
+		CK( cudaStreamCreateWithFlags( &c->stream, cudaStreamNonBlocking ) ) ;
+		CK( cudaEventCreate( &c->ev0 ) ) ; CK( cudaEventCreate( &c->ev1 ) ) ;
+		c->d_pick = dalloc<uint32_t>( c, 1 ) ;
+		c->d_counter = dalloc<unsigned long long>( c, 1 ) ;
+		*out = c ;
+		return 0 ;
+	} catch ( const std::exception& e ) {
+		g_init_error = e.what() ;
+		delete c ;
+		cudaGetLastError() ;
+		return 1 ;
+	}
+}
+
+void rtx_shutdown( rtx_ctx* c ) {
+	if ( ! c ) return ;
+	cudaSetDevice( c->device ) ;
+	cudaStreamSynchronize( c->stream ) ;
+	for ( Mesh& m : c->meshes ) {
+		dfree( c, m.vces, 3*size_t( m.nv ) ) ; dfree( c, m.ices, 3*size_t( m.nt ) ) ; dfree( c, m.tris, 3*size_t( m.nt ) ) ;
+		lbvh_free( c, m.bvh ) ;
+	}
+	lbvh_free( c, c->tlas ) ;
+	dfree( c, c->d_trav, c->n_things_dev ) ; dfree( c, c->d_shade, c->n_things_dev ) ;
+	dfree( c, c->d_tb_lo, c->n_things_dev ) ; dfree( c, c->d_tb_hi, c->n_things_dev ) ;
+	dfree( c, c->d_tp_lo, c->n_things_dev ) ; dfree( c, c->d_tp_hi, c->n_things_dev ) ;
+	free_frame( c ) ;
+	dfree( c, c->d_pick, 1 ) ; dfree( c, c->d_counter, 1 ) ;
+	cudaEventDestroy( c->ev0 ) ; cudaEventDestroy( c->ev1 ) ;
+	cudaStreamDestroy( c->stream ) ;
+	delete c ;
+}
+
+const char* rtx_last_error( const rtx_ctx* c ) { return c ? c->err.c_str() : g_init_error.c_str() ; }
+
+int rtx_mesh_create( rtx_ctx* c, const float* xyz, uint32_t nv, const uint32_t* idx, uint32_t nt, uint32_t* mesh_id ) {
+	RTX_TRY( c )
+	CK( cudaSetDevice( c->device ) ) ;
+	if ( ! xyz || ! idx || nv == 0 || nt == 0 ) throw std::runtime_error( "rtx_mesh_create: empty mesh" ) ;
+	if ( nt>= ( 1u<<29 ) ) throw std::runtime_error( "rtx_mesh_create: more than 2^29 triangles in one mesh" ) ;
+	for ( size_t k = 0 ; k<3*size_t( nt ) ; k++ )
+		if ( idx[k]>=nv ) throw std::runtime_error( "rtx_mesh_create: index out of bounds" ) ;   // optx/object.cxx:62-67
+	Mesh m ;
+	m.nv = nv ; m.nt = nt ;
+	m.vces = dalloc<float>( c, 3*size_t( nv ) ) ; m.ices = dalloc<uint32_t>( c, 3*size_t( nt ) ) ; m.tris = dalloc<q4>( c, 3*size_t( nt ) ) ;
+	CK( cudaMemcpyAsync( m.vces, xyz, sizeof( float )*3*nv, cudaMemcpyHostToDevice, c->stream ) ) ;
+	CK( cudaMemcpyAsync( m.ices, idx, sizeof( uint32_t )*3*size_t( nt ), cudaMemcpyHostToDevice, c->stream ) ) ;
+	q4* plo = dalloc<q4>( c, nt ) ; q4* phi = dalloc<q4>( c, nt ) ;
+	CK( cudaEventRecord( c->ev0, c->stream ) ) ;
+	k_tri_bounds<<<( nt+255 )/256, 256, 0, c->stream>>>( m.vces, m.ices, nt, plo, phi ) ;
+	c->launches += 1 ;
+	lbvh_build( c, m.bvh, plo, phi, nt ) ;
+	k_pack_tris<<<( nt+255 )/256, 256, 0, c->stream>>>( m.vces, m.ices, m.bvh.order, nt, m.tris ) ;
+	c->launches += 1 ;
+	CK( cudaGetLastError() ) ;
+	CK( cudaEventRecord( c->ev1, c->stream ) ) ;
+	CK( cudaStreamSynchronize( c->stream ) ) ;
+	float ms = 0.f ;
+	CK( cudaEventElapsedTime( &ms, c->ev0, c->ev1 ) ) ;
+	c->ms_blas += ms ;
+	dfree( c, plo, nt ) ; dfree( c, phi, nt ) ;
+	*mesh_id = uint32_t( c->meshes.size() ) ;
+	c->meshes.push_back( m ) ;
+	RTX_END( c )
+}
+
+int rtx_sphere_create( rtx_ctx* c, uint32_t* mesh_id ) {
+	RTX_TRY( c )
+	Mesh m ;
+	m.analytic = true ;
+	*mesh_id = uint32_t( c->meshes.size() ) ;
+	c->meshes.push_back( m ) ;
+	RTX_END( c )
+}
+
+int rtx_thing_add( rtx_ctx* c, uint32_t mesh_id, const rtx_optics* optics, uint32_t* thing_id ) {
+	RTX_TRY( c )
+	if ( mesh_id>=c->meshes.size() ) throw std::runtime_error( "rtx_thing_add: unknown mesh" ) ;
+	if ( optics->type<0 || optics->type>2 ) throw std::runtime_error( "rtx_thing_add: unknown optics type" ) ;
+	ThingHost th ;
+	th.mesh = mesh_id ; th.optics = *optics ;
+	const float ident[12] = { 1, 0, 0, 0,  0, 1, 0, 0,  0, 0, 1, 0 } ;   // optx/scene.cxx:183-188
+	memcpy( th.xf, ident, sizeof( ident ) ) ;
+	*thing_id = uint32_t( c->things.size() ) ;
+	c->things.push_back( th ) ;
+	RTX_END( c )
+}
+
+int rtx_thing_set_xf( rtx_ctx* c, uint32_t thing_id, const float xf[12] ) {
+	RTX_TRY( c )
+	if ( thing_id>=c->things.size() ) throw std::runtime_error( "rtx_thing_set_xf: unknown thing" ) ;
+	memcpy( c->things[thing_id].xf, xf, sizeof( float )*12 ) ;
+	RTX_END( c )
+}
+
+int rtx_thing_get_xf( rtx_ctx* c, uint32_t thing_id, float xf[12] ) {
+	RTX_TRY( c )
+	if ( thing_id>=c->things.size() ) throw std::runtime_error( "rtx_thing_get_xf: unknown thing" ) ;
+	memcpy( xf, c->things[thing_id].xf, sizeof( float )*12 ) ;
+	RTX_END( c )
+}
+
+int rtx_thing_set_optics( rtx_ctx* c, uint32_t thing_id, const rtx_optics* optics ) {
+	RTX_TRY( c )
+	if ( thing_id>=c->things.size() ) throw std::runtime_error( "rtx_thing_set_optics: unknown thing" ) ;
+	if ( optics->type<0 || optics->type>2 ) throw std::runtime_error( "rtx_thing_set_optics: unknown optics type" ) ;
+	c->things[thing_id].optics = *optics ;
+	RTX_END( c )
+}
+
+int rtx_accel_build( rtx_ctx* c ) {
+	RTX_TRY( c )
+	CK( cudaSetDevice( c->device ) ) ;
+	CK( cudaEventRecord( c->ev0, c->stream ) ) ;
+	upload_things( c ) ;
+	const uint32_t n = c->n_things_dev ;
+	if ( n ) lbvh_build( c, c->tlas, c->d_tp_lo, c->d_tp_hi, n ) ;
+	else     lbvh_free( c, c->tlas ) ;
+	CK( cudaEventRecord( c->ev1, c->stream ) ) ;
+	CK( cudaStreamSynchronize( c->stream ) ) ;
+	CK( cudaEventElapsedTime( &c->ms_tlas, c->ev0, c->ev1 ) ) ;
+	c->built = true ;
+	RTX_END( c )
+}
+
+int rtx_accel_refit( rtx_ctx* c ) {
+	RTX_TRY( c )
+	CK( cudaSetDevice( c->device ) ) ;
+	if ( ! c->built || c->things.size() != c->tlas.n )
+		throw std::runtime_error( "rtx_accel_refit: thing count changed since rtx_accel_build" ) ;
+	CK( cudaEventRecord( c->ev0, c->stream ) ) ;
+	upload_things( c ) ;
+	if ( c->tlas.n ) lbvh_refit( c, c->tlas, c->d_tp_lo, c->d_tp_hi ) ;
+	CK( cudaEventRecord( c->ev1, c->stream ) ) ;
+	CK( cudaStreamSynchronize( c->stream ) ) ;
+	CK( cudaEventElapsedTime( &c->ms_tlas, c->ev0, c->ev1 ) ) ;
+	RTX_END( c )
+}
+
+int rtx_resize( rtx_ctx* c, uint32_t w, uint32_t h ) {
+	RTX_TRY( c )
+	CK( cudaSetDevice( c->device ) ) ;
+	if ( w == 0 || h == 0 || uint64_t( w )*h>=( 1ull<<31 ) ) throw std::runtime_error( "rtx_resize: bad image size" ) ;
+	free_frame( c ) ;
+	c->w = w ; c->h = h ;
+	const size_t np = size_t( w )*h ;
+	c->d_accum = dalloc<uint64_t>( c, 4*np ) ; c->d_raw = dalloc<float>( c, 3*np ) ; c->d_rpp = dalloc<uint32_t>( c, np ) ;
+	c->d_image = dalloc<uchar4>( c, np ) ; c->d_hit_id = dalloc<int64_t>( c, np ) ; c->d_hit_t = dalloc<float>( c, np ) ;
+	c->d_normals = dalloc<float>( c, 3*np ) ; c->d_albedos = dalloc<float>( c, 3*np ) ;
+	CK( cudaMemsetAsync( c->d_accum, 0, 4*np*sizeof( uint64_t ), c->stream ) ) ;
+	CK( cudaMemsetAsync( c->d_raw, 0, 3*np*sizeof( float ), c->stream ) ) ;
+	CK( cudaMemsetAsync( c->d_rpp, 0, np*sizeof( uint32_t ), c->stream ) ) ;
+	CK( cudaMemsetAsync( c->d_normals, 0, 3*np*sizeof( float ), c->stream ) ) ;
+	CK( cudaMemsetAsync( c->d_albedos, 0, 3*np*sizeof( float ), c->stream ) ) ;
+	CK( cudaStreamSynchronize( c->stream ) ) ;
+	RTX_END( c )
+}
+
+int rtx_render( rtx_ctx* c, const rtx_params* p ) {
+	RTX_TRY( c )
+	CK( cudaSetDevice( c->device ) ) ;
+	if ( p->accumulate ) throw std::runtime_error( "rtx_render: accumulate needs rtx_render_accumulate + rtx_resolve" ) ;
+	do_render( c, p, true ) ;
+	RTX_END( c )
+}
+
+int rtx_render_accumulate( rtx_ctx* c, const rtx_params* p ) {
+	RTX_TRY( c )
+	CK( cudaSetDevice( c->device ) ) ;
+	do_render( c, p, false ) ;
+	RTX_END( c )
+}
+
+int rtx_resolve( rtx_ctx* c, uint64_t total_spp ) {
+	RTX_TRY( c )
+	CK( cudaSetDevice( c->device ) ) ;
+	if ( c->w == 0 ) throw std::runtime_error( "rtx_resolve: no frame (call rtx_resize)" ) ;
+	do_resolve( c, total_spp ) ;
+	CK( cudaStreamSynchronize( c->stream ) ) ;
+	RTX_END( c )
+}
+
+int rtx_pick( rtx_ctx* c, const rtx_params* p, uint32_t x, uint32_t y, uint32_t* thing_id ) {
+	RTX_TRY( c )
+	CK( cudaSetDevice( c->device ) ) ;
+	const FrameArgs a = frame_args( c, p ) ;
+	if ( x>=a.w || y>=a.h ) throw std::runtime_error( "rtx_pick: pixel outside the image" ) ;
+	k_pick<<<1, 32, 0, c->stream>>>( a, x, y, c->d_pick ) ;
+	c->launches += 1 ;
+	CK( cudaGetLastError() ) ;
+	CK( cudaMemcpyAsync( thing_id, c->d_pick, sizeof( uint32_t ), cudaMemcpyDeviceToHost, c->stream ) ) ;
+	CK( cudaStreamSynchronize( c->stream ) ) ;
+	RTX_END( c )
+}
+
+int rtx_postproc( rtx_ctx* c, int kind ) {
+	RTX_TRY( c )
+	CK( cudaSetDevice( c->device ) ) ;
+	if ( c->w == 0 ) throw std::runtime_error( "rtx_postproc: no frame (call rtx_resize)" ) ;
+	if ( kind != RTX_PP_NONE && kind != RTX_PP_SRGB ) throw std::runtime_error( "rtx_postproc: unknown kind" ) ;
+	const uint32_t np = c->w*c->h ;
+	k_postproc<<<( np+255 )/256, 256, 0, c->stream>>>( c->d_raw, c->d_image, np, kind == RTX_PP_SRGB ) ;
+	c->launches += 1 ;
+	CK( cudaGetLastError() ) ;
+	CK( cudaStreamSynchronize( c->stream ) ) ;
+	RTX_END( c )
+}
+
+int rtx_postproc_dev( rtx_ctx* c, int kind, const void* src, void* dst, int w, int h ) {
+	RTX_TRY( c )
+	CK( cudaSetDevice( c->device ) ) ;
+	if ( kind != RTX_PP_NONE && kind != RTX_PP_SRGB ) throw std::runtime_error( "rtx_postproc_dev: unknown kind" ) ;
+	if ( w<1 || h<1 ) throw std::runtime_error( "rtx_postproc_dev: bad size" ) ;
+	const uint32_t np = uint32_t( w )*uint32_t( h ) ;
+	k_postproc<<<( np+255 )/256, 256, 0, c->stream>>>( static_cast<const float*>( src ), static_cast<uchar4*>( dst ), np, kind == RTX_PP_SRGB ) ;
+	c->launches += 1 ;
+	CK( cudaGetLastError() ) ;
+	CK( cudaStreamSynchronize( c->stream ) ) ;
+	RTX_END( c )
+}
+
+int rtx_primary_hits( rtx_ctx* c, const rtx_params* p ) {
+	RTX_TRY( c )
+	CK( cudaSetDevice( c->device ) ) ;
+	const FrameArgs a = frame_args( c, p ) ;
+	k_primary_hits<<<tile_grid( a.w, a.h ), RTX_BLOCK, 0, c->stream>>>( a ) ;
+	c->launches += 1 ;
+	CK( cudaGetLastError() ) ;
+	CK( cudaStreamSynchronize( c->stream ) ) ;
+	RTX_END( c )
+}
+
+int rtx_trace_rays( rtx_ctx* c, uint32_t n, const float* ori, const float* dir, float tmin, int brute, int64_t* id_out, float* t_out ) {
+	RTX_TRY( c )
+	CK( cudaSetDevice( c->device ) ) ;
+	if ( ! c->built ) throw std::runtime_error( "rtx_trace_rays: acceleration structure not built" ) ;
+	if ( n == 0 ) return 0 ;
+	float* d_o = dalloc<float>( c, 3*size_t( n ) ) ; float* d_d = dalloc<float>( c, 3*size_t( n ) ) ;
+	int64_t* d_id = dalloc<int64_t>( c, n ) ; float* d_t = dalloc<float>( c, n ) ;
+	CK( cudaMemcpyAsync( d_o, ori, sizeof( float )*3*n, cudaMemcpyHostToDevice, c->stream ) ) ;
+	CK( cudaMemcpyAsync( d_d, dir, sizeof( float )*3*n, cudaMemcpyHostToDevice, c->stream ) ) ;
+	k_trace_rays<<<( n+RTX_BLOCK-1 )/RTX_BLOCK, RTX_BLOCK, 0, c->stream>>>( scene_dev( c ), n, d_o, d_d, tmin, brute, d_id, d_t ) ;
+	c->launches += 1 ;
+	CK( cudaGetLastError() ) ;
+	CK( cudaMemcpyAsync( id_out, d_id, sizeof( int64_t )*n, cudaMemcpyDeviceToHost, c->stream ) ) ;
+	if ( t_out ) CK( cudaMemcpyAsync( t_out, d_t, sizeof( float )*n, cudaMemcpyDeviceToHost, c->stream ) ) ;
+	CK( cudaStreamSynchronize( c->stream ) ) ;
+	dfree( c, d_o, 3*size_t( n ) ) ; dfree( c, d_d, 3*size_t( n ) ) ; dfree( c, d_id, n ) ; dfree( c, d_t, n ) ;
+	RTX_END( c )
+}
+
+int rtx_read( rtx_ctx* c, int buffer, void* host_dst, size_t bytes ) {
+	RTX_TRY( c )
+	CK( cudaSetDevice( c->device ) ) ;
+	const BufInfo b = buffer_of( c, buffer ) ;
+	if ( ! b.ptr || bytes>b.bytes ) throw std::runtime_error( "rtx_read: buffer missing or request too large" ) ;
+	CK( cudaMemcpyAsync( host_dst, b.ptr, bytes, cudaMemcpyDeviceToHost, c->stream ) ) ;
+	CK( cudaStreamSynchronize( c->stream ) ) ;
+	RTX_END( c )
+}
+
+int rtx_write( rtx_ctx* c, int buffer, const void* host_src, size_t bytes ) {
+	RTX_TRY( c )
+	CK( cudaSetDevice( c->device ) ) ;
+	const BufInfo b = buffer_of( c, buffer ) ;
+	if ( ! b.ptr || bytes>b.bytes ) throw std::runtime_error( "rtx_write: buffer missing or request too large" ) ;
+	CK( cudaMemcpyAsync( b.ptr, host_src, bytes, cudaMemcpyHostToDevice, c->stream ) ) ;
+	CK( cudaStreamSynchronize( c->stream ) ) ;
+	RTX_END( c )
+}
+
+int rtx_device_ptr( rtx_ctx* c, int buffer, void** dev_ptr, size_t* bytes ) {
+	RTX_TRY( c )
+	const BufInfo b = buffer_of( c, buffer ) ;
+	if ( ! b.ptr ) throw std::runtime_error( "rtx_device_ptr: no frame (call rtx_resize)" ) ;
+	*dev_ptr = b.ptr ;
+	if ( bytes ) *bytes = b.bytes ;
+	RTX_END( c )
+}
+
+int rtx_stats_get( rtx_ctx* c, rtx_stats* out ) {
+	RTX_TRY( c )
+	CK( cudaSetDevice( c->device ) ) ;
+	memset( out, 0, sizeof( *out ) ) ;
+	if ( c->d_accum ) {
+		const uint32_t np = c->w*c->h ;
+		CK( cudaMemsetAsync( c->d_counter, 0, sizeof( unsigned long long ), c->stream ) ) ;
+		k_sum_segments<<<min( 1184u, ( np+255u )/256u ), 256, 0, c->stream>>>( c->d_accum, np, c->d_counter ) ;
+		c->launches += 1 ;
+		unsigned long long s = 0 ;
+		CK( cudaMemcpyAsync( &s, c->d_counter, sizeof( s ), cudaMemcpyDeviceToHost, c->stream ) ) ;
+		CK( cudaStreamSynchronize( c->stream ) ) ;
+		out->segments = s ;
+	}
+	out->paths = c->paths ;
+	out->ms_render = c->ms_render ; out->ms_build_blas = c->ms_blas ; out->ms_build_tlas = c->ms_tlas ;
+	out->launches = c->launches ;
+	out->n_things = uint32_t( c->things.size() ) ; out->n_meshes = uint32_t( c->meshes.size() ) ;
+	for ( const Mesh& m : c->meshes ) out->n_triangles += m.nt ;
+	for ( const ThingHost& t : c->things ) out->n_triangles_instanced += c->meshes[t.mesh].nt ;
+	out->bytes_device = c->bytes ;
+	RTX_END( c )
+}
+
+int rtx_last_render_ms( rtx_ctx* c, float* ms ) {
+	RTX_TRY( c )
+	*ms = c->ms_render ;
+	RTX_END( c )
+}
+
+} // extern "C"

@@ -1,0 +1,510 @@
+// rtx_core.cuh -- device-side core of the B200 path tracer: vector math, the keyed
+// random stream, two-level LBVH traversal with exact primitive tests, and the three
+// scattering models.  Everything here is __host__ __device__ so that the SAME source can
+// be driven serially on the CPU by the development harness in tests/hostemu (no GPU in
+// the build container); the product library only ever runs it in kernels.
+//
+// Arithmetic contract ("float contract"): this translation unit is
+// compiled with -fmad=false, so every + - * / sqrt below is one IEEE rounding, in the
+// order written; the only fused operations are the explicit fmaf() calls of the
+// box test, which is conservative and never decides a result.  Reference semantics
+// followed (file:line under /root/reference): rtow.cxx:34-49 (trace), sphere.h:20-48,
+// things.h:22-36, optics.h:11-75, v.h:42-62, camera.h:25-31, rtow.cxx:112-113;
+// triangle mode: optx/optics_i.cu:40-82, :259-267.
+#pragma once
+
+#include <stdint.h>
+#include <math.h>
+#include <float.h>
+
+#if defined( __CUDACC__ )
+#define RTX_HD __host__ __device__ __forceinline__
+#else
+#define RTX_HD inline
+#endif
+
+#if defined( __CUDA_ARCH__ )
+#define RTX_LDG( p ) __ldg( p )
+#else
+#define RTX_LDG( p ) ( *( p ) )
+#endif
+
+namespace rtx {
+
+// ----------------------------------------------------------------------------- vectors
+struct f3 { float x, y, z ; } ;
+struct d3 { double x, y, z ; } ;
+
+RTX_HD f3 mk3( float x, float y, float z ) { f3 v ; v.x = x ; v.y = y ; v.z = z ; return v ; }
+RTX_HD d3 mk3( double x, double y, double z ) { d3 v ; v.x = x ; v.y = y ; v.z = z ; return v ; }
+
+#define RTX_VEC_OPS( V, S )                                                                                  \
+RTX_HD V operator + ( const V& u, const V& v ) { return mk3( u.x+v.x, u.y+v.y, u.z+v.z ) ; }                 \
+RTX_HD V operator - ( const V& u, const V& v ) { return mk3( u.x-v.x, u.y-v.y, u.z-v.z ) ; }                 \
+RTX_HD V operator - ( const V& u )             { return mk3( -u.x, -u.y, -u.z ) ; }                          \
+RTX_HD V operator * ( const V& u, const V& v ) { return mk3( u.x*v.x, u.y*v.y, u.z*v.z ) ; }                 \
+RTX_HD V operator * ( S t, const V& v )        { return mk3( t*v.x, t*v.y, t*v.z ) ; }                       \
+RTX_HD S dot( const V& u, const V& v )         { return u.x*v.x+u.y*v.y+u.z*v.z ; }                          \
+RTX_HD V cross( const V& u, const V& v )       { return mk3( u.y*v.z-u.z*v.y, u.z*v.x-u.x*v.z, u.x*v.y-u.y*v.x ) ; }
+RTX_VEC_OPS( f3, float )
+RTX_VEC_OPS( d3, double )
+#undef RTX_VEC_OPS
+
+// v.h:46,51: division is multiplication by the reciprocal; unitV(v) = v/len(v)
+RTX_HD f3 unitV( const f3& v ) { return ( 1.f/sqrtf( dot( v, v ) ) )*v ; }
+RTX_HD d3 unitV( const d3& v ) { return ( 1./sqrt( dot( v, v ) ) )*v ; }
+RTX_HD d3 wide( const f3& v )   { return mk3( double( v.x ), double( v.y ), double( v.z ) ) ; }
+RTX_HD f3 narrow( const d3& v ) { return mk3( float( v.x ), float( v.y ), float( v.z ) ) ; }
+
+// row-major 3x4 affine map, written order = contract
+RTX_HD d3 xfpoint( const double* m, const d3& p ) {
+	return mk3( p.x*m[0]+p.y*m[1]+p.z*m[2]+m[3], p.x*m[4]+p.y*m[5]+p.z*m[6]+m[7], p.x*m[8]+p.y*m[9]+p.z*m[10]+m[11] ) ;
+}
+RTX_HD d3 xfvec( const double* m, const d3& p ) {
+	return mk3( p.x*m[0]+p.y*m[1]+p.z*m[2], p.x*m[4]+p.y*m[5]+p.z*m[6], p.x*m[8]+p.y*m[9]+p.z*m[10] ) ;
+}
+
+// ----------------------------------------------------------------------------- random stream
+// Stream of path (pixel, sample) = PCG32 (XSH-RR 64/32) started at a splitmix64 hash of
+// (seed, pixel, sample): any partition of the samples over lanes or GPUs sees the same
+// numbers.  Replaces Frand48 (optx/frand48.h:17-35), whose stream is per pixel only.
+struct Pcg {
+	uint64_t state ;
+	RTX_HD static uint64_t mix( uint64_t z ) {
+		z = ( z^( z>>30 ) )*0xBF58476D1CE4E5B9ull ;
+		z = ( z^( z>>27 ) )*0x94D049BB133111EBull ;
+		return z^( z>>31 ) ;
+	}
+	RTX_HD void seed( uint64_t seed, uint32_t pixel, uint32_t sample ) {
+		state = mix( ( ( uint64_t( pixel )<<32 )|uint64_t( sample ) )^( seed*0x9E3779B97F4A7C15ull ) ) ;
+	}
+	RTX_HD uint32_t bits() {
+		const uint64_t old = state ;
+		state = old*6364136223846793005ull+1442695040888963407ull ;
+		const uint32_t xs  = uint32_t( ( ( old>>18 )^old )>>27 ) ;
+		const uint32_t rot = uint32_t( old>>59 ) ;
+		return ( xs>>rot )|( xs<<( ( 32-rot )&31 ) ) ;
+	}
+	// util.h:12 rnd(): here 24 random bits, exact in float
+	RTX_HD float rnd() { return float( bits()>>8 )*( 1.f/16777216.f ) ; }
+	// util.h:13
+	RTX_HD float rnd( float min, float max ) { return min+rnd()*( max-min ) ; }
+	// v.h:30-31 as g++ sequences it: z, y, x
+	RTX_HD f3 rndV( float min, float max ) { const float z = rnd( min, max ) ; const float y = rnd( min, max ) ; const float x = rnd( min, max ) ; return mk3( x, y, z ) ; }
+	// v.h:53
+	RTX_HD f3 rndVin1sphere() { while ( true ) { const f3 v = rndV( -1.f, 1.f ) ; if ( 1.f>dot( v, v ) ) return v ; } }
+	// v.h:55
+	RTX_HD f3 rndVon1sphere() { return unitV( rndVin1sphere() ) ; }
+	// v.h:59 as g++ sequences it: y, x
+	RTX_HD f3 rndVin1disk() { while ( true ) { const float y = rnd( -1.f, 1.f ) ; const float x = rnd( -1.f, 1.f ) ; const f3 v = mk3( x, y, 0.f ) ; if ( 1.f>dot( v, v ) ) return v ; } }
+} ;
+
+// ----------------------------------------------------------------------------- scene (device view)
+struct q4 { float x, y, z, w ; } ;   // 16-byte record, bit-compatible with float4
+
+// BVH2 node, 64 bytes = 4 x 16-byte records (vector loads):
+//   r0 = child0.lo.xyz, asfloat(child0 ref)   r1 = child0.hi.xyz, asfloat(child1 ref)
+//   r2 = child1.lo.xyz, -                     r3 = child1.hi.xyz, -
+// child ref >= 0: inner node index; < 0: leaf, ~ref = first<<2 | (count-1)
+#define RTX_NODE_RECS 4
+#define RTX_LEAF_MAX  4
+
+// per-thing record read by traversal (128 bytes)
+struct ThingTrav {
+	double     inv[12] ;   // world->object (mesh); analytic sphere: inv[0..3] = cx, cy, cz, r
+	const q4*  nodes ;     // mesh LBVH
+	const q4*  tris ;      // mesh triangles in leaf order: (v0, asfloat(prim)), (e1,-), (e2,-)
+	int32_t    kind ;      // 0 analytic sphere, 1 mesh instance
+	uint32_t   n_tris ;
+	int32_t    pad[2] ;
+} ;
+
+// per-thing record read by shading (144 bytes)
+struct ThingShade {
+	double          xf[12] ;  // object->world
+	float           albedo[3], fuzz ;
+	float           index ;
+	int32_t         type ;    // rtx_optics type
+	int32_t         kind ;
+	int32_t         pad ;
+	const float*    vces ;    // mesh vertices (xyz) and indices as uploaded
+	const uint32_t* ices ;
+} ;
+
+struct SceneDev {
+	const q4*         tlas_nodes ;
+	const uint32_t*   tlas_order ;   // leaf slot -> thing id
+	const ThingTrav*  trav ;
+	const ThingShade* shade ;
+	uint32_t          n_things ;
+} ;
+
+struct CameraDev { f3 eye, u, v, hvec, wvec, dvec ; float aperture ; } ;
+
+struct HitRec {
+	float   t ;
+	int32_t thing ;   // -1: miss
+	int32_t prim ;    // -1: analytic
+	float   u, v ;    // barycentrics (mesh)
+} ;
+
+// shading frame of a hit
+struct Frame { f3 p, normal ; bool facing ; } ;
+
+RTX_HD q4 ldq( const q4* p ) {
+#if defined( __CUDA_ARCH__ )
+	const float4 v = __ldg( reinterpret_cast<const float4*>( p ) ) ;
+	q4 r ; r.x = v.x ; r.y = v.y ; r.z = v.z ; r.w = v.w ; return r ;
+#else
+	return *p ;
+#endif
+}
+// __ldg has no pointer overload: read the 8 bytes as an integer
+template <class T> RTX_HD const T* ldptr( const T* const* pp ) {
+#if defined( __CUDA_ARCH__ )
+	return reinterpret_cast<const T*>( __ldg( reinterpret_cast<const unsigned long long*>( pp ) ) ) ;
+#else
+	return *pp ;
+#endif
+}
+RTX_HD int32_t asint( float f ) {
+#if defined( __CUDA_ARCH__ )
+	return __float_as_int( f ) ;
+#else
+	union { float f ; int32_t i ; } c ; c.f = f ; return c.i ;
+#endif
+}
+RTX_HD float asfloat( int32_t i ) {
+#if defined( __CUDA_ARCH__ )
+	return __int_as_float( i ) ;
+#else
+	union { float f ; int32_t i ; } c ; c.i = i ; return c.f ;
+#endif
+}
+
+// ----------------------------------------------------------------------------- primitive tests
+// sphere.h:21-38 verbatim, in double on the widened float ray: the smallest root not
+// below tmin.  (things.h:27-33 keeps it when it does not exceed the best t so far.)
+RTX_HD bool sphere_root( const d3& center, double radius, const d3& ori, const d3& dir, double tmin, double& t ) {
+	const d3 o = ori-center ;
+	const double a = dot( dir, dir ) ;
+	const double b = dot( dir, o ) ;
+	const double c = dot( o, o )-radius*radius ;
+	const double discriminant = b*b-a*c ;
+	if ( 0.>discriminant )
+		return false ;
+	const double x = sqrt( discriminant ) ;
+	t = ( -b-x )/a ;
+	if ( tmin>t ) {
+		t = ( -b+x )/a ;
+		if ( tmin>t )
+			return false ;
+	}
+	return true ;
+}
+
+// Moeller-Trumbore, two-sided, on the stored (v0, e1, e2) in object space; the origin is
+// the float pair hi+lo of the double-precision object-space origin.
+RTX_HD bool tri_test( const f3& v0, const f3& e1, const f3& e2, const f3& ohi, const f3& olo, const f3& d, float tmin, float& t, float& u, float& v ) {
+	const f3 p = cross( d, e2 ) ;
+	const float det = dot( e1, p ) ;
+	if ( det == 0.f )
+		return false ;
+	const float inv = 1.f/det ;
+	const f3 s = ( ohi-v0 )+olo ;
+	u = dot( s, p )*inv ;
+	if ( ! ( u>=0.f && u<=1.f ) )
+		return false ;
+	const f3 q = cross( s, e1 ) ;
+	v = dot( d, q )*inv ;
+	if ( ! ( v>=0.f && u+v<=1.f ) )
+		return false ;
+	t = dot( e2, q )*inv ;
+	return t>=tmin ;
+}
+
+// order-independent closest-hit rule = things.h:27-33 scanned in thing/primitive order:
+// smaller t wins, at exactly equal t the later-listed (thing, prim) wins
+RTX_HD bool better( float t, int32_t thing, int32_t prim, const HitRec& best ) {
+	return t<best.t || ( t == best.t && ( thing>best.thing || ( thing == best.thing && prim>best.prim ) ) ) ;
+}
+
+// ----------------------------------------------------------------------------- box test
+// Conservative slab test (boxes are padded at build time, the far bound carries a
+// relative slack): may visit too much, never too little.  This is the one place where
+// FMA is used on purpose.
+#define RTX_SLACK 1.0000038f
+RTX_HD float safe_rcp( float d ) {
+	const float big = 1e30f ;
+	return fabsf( d )>1e-30f ? 1.f/d : ( d<0.f ? -big : big ) ;   // -0.f counts as +
+}
+RTX_HD bool slab( const f3& lo, const f3& hi, const f3& idir, const f3& ood, float tmin, float tbest_s, float& tn ) {
+	const float x0 = fmaf( lo.x, idir.x, -ood.x ), x1 = fmaf( hi.x, idir.x, -ood.x ) ;
+	const float y0 = fmaf( lo.y, idir.y, -ood.y ), y1 = fmaf( hi.y, idir.y, -ood.y ) ;
+	const float z0 = fmaf( lo.z, idir.z, -ood.z ), z1 = fmaf( hi.z, idir.z, -ood.z ) ;
+	tn = fmaxf( fmaxf( fminf( x0, x1 ), fminf( y0, y1 ) ), fmaxf( fminf( z0, z1 ), tmin ) ) ;
+	const float tf = fminf( fminf( fmaxf( x0, x1 ), fmaxf( y0, y1 ) ), fminf( fmaxf( z0, z1 ), tbest_s ) ) ;
+	return tn<=tf*RTX_SLACK ;
+}
+
+// ----------------------------------------------------------------------------- traversal
+// One stack for both levels: entering a mesh pushes RTX_STK_RETURN, popping it restores
+// the world-space ray.  Stack is a policy: shared memory + overflow on the device.
+#define RTX_STK_RETURN 0x7fffffff
+
+template <class Stack>
+RTX_HD void closest( const SceneDev& S, const f3& o, const f3& d, float tmin, Stack& st, HitRec& best, uint32_t* visits = nullptr ) {
+	best.t = INFINITY ; best.thing = -1 ; best.prim = -1 ; best.u = 0.f ; best.v = 0.f ;
+	if ( S.n_things == 0 )
+		return ;
+	float tbest_s = INFINITY ;
+
+	// current-level ray
+	f3 idir = mk3( safe_rcp( d.x ), safe_rcp( d.y ), safe_rcp( d.z ) ) ;
+	f3 ood  = mk3( o.x*idir.x, o.y*idir.y, o.z*idir.z ) ;
+	const q4* nodes = S.tlas_nodes ;
+	// mesh-level state
+	f3 ohi = o, olo = mk3( 0.f, 0.f, 0.f ), dd = d ;
+	const q4* tris = nullptr ;
+	int32_t thing = -1 ;
+
+	st.reset() ;
+	int32_t cur = 0 ;   // root
+	while ( true ) {
+		if ( cur>=0 && cur != RTX_STK_RETURN ) {
+			// inner node: test both children
+			const q4* n = nodes+size_t( cur )*RTX_NODE_RECS ;
+			const q4 r0 = ldq( n ), r1 = ldq( n+1 ), r2 = ldq( n+2 ), r3 = ldq( n+3 ) ;
+			if ( visits ) ( *visits )++ ;
+			float t0, t1 ;
+			const bool h0 = slab( mk3( r0.x, r0.y, r0.z ), mk3( r1.x, r1.y, r1.z ), idir, ood, tmin, tbest_s, t0 ) ;
+			const bool h1 = slab( mk3( r2.x, r2.y, r2.z ), mk3( r3.x, r3.y, r3.z ), idir, ood, tmin, tbest_s, t1 ) ;
+			const int32_t c0 = asint( r0.w ), c1 = asint( r1.w ) ;
+			if ( h0 && h1 ) {
+				const bool swap = t1<t0 ;
+				cur = swap ? c1 : c0 ;
+				st.push( swap ? c0 : c1 ) ;
+				continue ;
+			}
+			if ( h0 ) { cur = c0 ; continue ; }
+			if ( h1 ) { cur = c1 ; continue ; }
+		} else if ( cur<0 ) {
+			// leaf
+			const uint32_t ref = uint32_t( ~cur ) ;
+			const uint32_t first = ref>>2, count = ( ref&3u )+1u ;
+			if ( tris ) {
+				for ( uint32_t k = 0 ; k<count ; k++ ) {
+					const q4* T = tris+size_t( first+k )*3 ;
+					const q4 a = ldq( T ), b = ldq( T+1 ), c = ldq( T+2 ) ;
+					float t, u, v ;
+					if ( tri_test( mk3( a.x, a.y, a.z ), mk3( b.x, b.y, b.z ), mk3( c.x, c.y, c.z ), ohi, olo, dd, tmin, t, u, v ) ) {
+						const int32_t prim = asint( a.w ) ;
+						if ( better( t, thing, prim, best ) ) {
+							best.t = t ; best.thing = thing ; best.prim = prim ; best.u = u ; best.v = v ;
+							tbest_s = t*RTX_SLACK ;
+						}
+					}
+				}
+			} else {
+				// top level: count is 1 by construction
+				const int32_t k = int32_t( RTX_LDG( S.tlas_order+first ) ) ;
+				const ThingTrav* tt = S.trav+k ;
+				const double m0 = RTX_LDG( tt->inv+0 ), m1 = RTX_LDG( tt->inv+1 ), m2 = RTX_LDG( tt->inv+2 ), m3 = RTX_LDG( tt->inv+3 ) ;
+				if ( RTX_LDG( &tt->kind ) == 0 ) {
+					double td ;
+					if ( sphere_root( mk3( m0, m1, m2 ), m3, wide( o ), wide( d ), double( tmin ), td ) ) {
+						const float t = float( td ) ;
+						if ( better( t, k, -1, best ) ) {
+							best.t = t ; best.thing = k ; best.prim = -1 ;
+							tbest_s = t*RTX_SLACK ;
+						}
+					}
+				} else {
+					// enter the mesh: object-space ray, origin in double carried as hi+lo
+					double m[12] ;
+					m[0] = m0 ; m[1] = m1 ; m[2] = m2 ; m[3] = m3 ;
+					for ( int j = 4 ; j<12 ; j++ ) m[j] = RTX_LDG( tt->inv+j ) ;
+					const d3 od = xfpoint( m, wide( o ) ) ;
+					ohi = narrow( od ) ;
+					olo = narrow( od-wide( ohi ) ) ;
+					dd  = narrow( xfvec( m, wide( d ) ) ) ;
+					idir = mk3( safe_rcp( dd.x ), safe_rcp( dd.y ), safe_rcp( dd.z ) ) ;
+					ood  = mk3( ohi.x*idir.x, ohi.y*idir.y, ohi.z*idir.z ) ;
+					nodes = ldptr( &tt->nodes ) ;
+					tris  = ldptr( &tt->tris ) ;
+					thing = k ;
+					st.push( RTX_STK_RETURN ) ;
+					cur = 0 ;
+					continue ;
+				}
+			}
+		} else {
+			// back to the top level
+			idir = mk3( safe_rcp( d.x ), safe_rcp( d.y ), safe_rcp( d.z ) ) ;
+			ood  = mk3( o.x*idir.x, o.y*idir.y, o.z*idir.z ) ;
+			nodes = S.tlas_nodes ; tris = nullptr ; thing = -1 ;
+		}
+		if ( st.empty() )
+			break ;
+		cur = st.pop() ;
+	}
+}
+
+// exhaustive scan (validation instrument; same tests, same tie rule, no boxes)
+RTX_HD void closest_brute( const SceneDev& S, const f3& o, const f3& d, float tmin, HitRec& best ) {
+	best.t = INFINITY ; best.thing = -1 ; best.prim = -1 ; best.u = 0.f ; best.v = 0.f ;
+	for ( uint32_t k = 0 ; k<S.n_things ; k++ ) {
+		const ThingTrav* tt = S.trav+k ;
+		if ( tt->kind == 0 ) {
+			double td ;
+			if ( sphere_root( mk3( tt->inv[0], tt->inv[1], tt->inv[2] ), tt->inv[3], wide( o ), wide( d ), double( tmin ), td ) ) {
+				const float t = float( td ) ;
+				if ( better( t, int32_t( k ), -1, best ) ) { best.t = t ; best.thing = int32_t( k ) ; best.prim = -1 ; }
+			}
+		} else {
+			const d3 od = xfpoint( tt->inv, wide( o ) ) ;
+			const f3 ohi = narrow( od ) ;
+			const f3 olo = narrow( od-wide( ohi ) ) ;
+			const f3 dd  = narrow( xfvec( tt->inv, wide( d ) ) ) ;
+			for ( uint32_t f = 0 ; f<tt->n_tris ; f++ ) {
+				const q4* T = tt->tris+size_t( f )*3 ;
+				const q4 a = ldq( T ), b = ldq( T+1 ), c = ldq( T+2 ) ;
+				float t, u, v ;
+				if ( tri_test( mk3( a.x, a.y, a.z ), mk3( b.x, b.y, b.z ), mk3( c.x, c.y, c.z ), ohi, olo, dd, tmin, t, u, v ) ) {
+					const int32_t prim = asint( a.w ) ;
+					if ( better( t, int32_t( k ), prim, best ) ) { best.t = t ; best.thing = int32_t( k ) ; best.prim = prim ; best.u = u ; best.v = v ; }
+				}
+			}
+		}
+	}
+}
+
+// ----------------------------------------------------------------------------- shading frame
+// sphere.h:40-45 (analytic) / optx/optics_i.cu:40-82, :259-267 (mesh), in double,
+// rounded once
+RTX_HD void frame_of( const SceneDev& S, const HitRec& h, const f3& o, const f3& d, float tmin, Frame& fr ) {
+	const ThingShade* ts = S.shade+h.thing ;
+	double m[12] ;
+	for ( int j = 0 ; j<12 ; j++ ) m[j] = RTX_LDG( ts->xf+j ) ;
+	const d3 dw = wide( d ) ;
+	const d3 center = mk3( m[3], m[7], m[11] ) ;
+	if ( h.prim<0 ) {
+		const double r = m[0] ;
+		double td = 0. ;
+		sphere_root( center, r, wide( o ), dw, double( tmin ), td ) ;
+		const d3 p = wide( o )+td*dw ;
+		const d3 outward = ( 1./r )*( p-center ) ;
+		fr.p = narrow( p ) ;
+		fr.facing = 0.>dot( dw, outward ) ;
+		fr.normal = narrow( fr.facing ? outward : -outward ) ;
+		return ;
+	}
+	const uint32_t* ices = ldptr( &ts->ices ) ;
+	const float*    vces = ldptr( &ts->vces ) ;
+	const uint32_t i0 = RTX_LDG( ices+3*size_t( h.prim ) ), i1 = RTX_LDG( ices+3*size_t( h.prim )+1 ), i2 = RTX_LDG( ices+3*size_t( h.prim )+2 ) ;
+	const d3 a = mk3( double( RTX_LDG( vces+3*size_t( i0 ) ) ), double( RTX_LDG( vces+3*size_t( i0 )+1 ) ), double( RTX_LDG( vces+3*size_t( i0 )+2 ) ) ) ;
+	const d3 b = mk3( double( RTX_LDG( vces+3*size_t( i1 ) ) ), double( RTX_LDG( vces+3*size_t( i1 )+1 ) ), double( RTX_LDG( vces+3*size_t( i1 )+2 ) ) ) ;
+	const d3 c = mk3( double( RTX_LDG( vces+3*size_t( i2 ) ) ), double( RTX_LDG( vces+3*size_t( i2 )+1 ) ), double( RTX_LDG( vces+3*size_t( i2 )+2 ) ) ) ;
+	const d3 A = xfpoint( m, a ), B = xfpoint( m, b ), C = xfpoint( m, c ) ;
+	const float w = 1.f-h.u-h.v ;
+	const d3 p = double( w )*A+double( h.u )*B+double( h.v )*C ;
+	d3 N = unitV( cross( B-A, C-A ) ) ;
+	if ( dot( dw, N )>0. )
+		N = -N ;
+	fr.p = narrow( p ) ;
+	fr.normal = narrow( N ) ;
+	fr.facing = 0.>dot( dw, p-center ) ;
+}
+
+// ----------------------------------------------------------------------------- scattering
+RTX_HD f3 reflect( const f3& v, const f3& n ) { return v-( 2.f*dot( v, n ) )*n ; }                                   // v.h:61
+RTX_HD f3 refract( const f3& v, const f3& n, float ratio ) {                                                        // v.h:62
+	const float theta = fminf( dot( -v, n ), 1.f ) ;
+	const f3 perpen = ratio*( v+theta*n ) ;
+	const f3 parall = ( -sqrtf( fabsf( 1.f-dot( perpen, perpen ) ) ) )*n ;
+	return perpen+parall ;
+}
+RTX_HD float schlick( float cos_theta, float ratio ) {                                                              // optics.h:74
+	float r0 = ( 1.f-ratio )/( 1.f+ratio ) ; r0 = r0*r0 ;
+	const float m = 1.f-cos_theta ;
+	const float m2 = m*m ;
+	return r0+( 1.f-r0 )*( ( m2*m2 )*m ) ;
+}
+
+// optics.h:15-24 (Diffuse), :34-40 (Reflect), :51-68 (Refract).  Returns false when
+// the path is absorbed.
+RTX_HD bool scatter( const ThingShade* ts, const f3& dir, const Frame& fr, Pcg& rng, f3& attened, f3& out ) {
+	const int32_t type = RTX_LDG( &ts->type ) ;
+	if ( type == 0 ) {
+		f3 dnew = fr.normal+rng.rndVon1sphere() ;
+		if ( fabsf( dnew.x )<1e-8f && fabsf( dnew.y )<1e-8f && fabsf( dnew.z )<1e-8f )   // util.h:8 kNear0
+			dnew = fr.normal ;
+		out = dnew ;
+		attened = mk3( RTX_LDG( ts->albedo ), RTX_LDG( ts->albedo+1 ), RTX_LDG( ts->albedo+2 ) ) ;
+		return true ;
+	}
+	if ( type == 1 ) {
+		const f3 r = reflect( unitV( dir ), fr.normal ) ;
+		out = r+RTX_LDG( &ts->fuzz )*rng.rndVin1sphere() ;
+		attened = mk3( RTX_LDG( ts->albedo ), RTX_LDG( ts->albedo+1 ), RTX_LDG( ts->albedo+2 ) ) ;
+		return dot( out, fr.normal )>0.f ;
+	}
+	const f3 d1V = unitV( dir ) ;
+	const float cos_theta = fminf( dot( -d1V, fr.normal ), 1.f ) ;
+	const float sin_theta = sqrtf( 1.f-cos_theta*cos_theta ) ;
+	const float index = RTX_LDG( &ts->index ) ;
+	const float ratio = fr.facing ? 1.f/index : index ;
+	const bool cannot = ratio*sin_theta>1.f ;
+	if ( cannot || schlick( cos_theta, ratio )>rng.rnd() )
+		out = reflect( d1V, fr.normal ) ;
+	else
+		out = refract( d1V, fr.normal, ratio ) ;
+	attened = mk3( 1.f, 1.f, 1.f ) ;
+	return true ;
+}
+
+// rtow.cxx:45-48
+RTX_HD f3 sky( const f3& dir ) {
+	const f3 unit = unitV( dir ) ;
+	const float t = .5f*( unit.y+1.f ) ;
+	return ( 1.f-t )*mk3( 1.f, 1.f, 1.f )+t*mk3( .5f, .7f, 1.f ) ;
+}
+
+// rtow.cxx:112-113 + camera.h:25-31
+RTX_HD void primary_ray( const CameraDev& cam, uint32_t x, uint32_t y, uint32_t w, uint32_t h, Pcg& rng, f3& ori, f3& dir ) {
+	const float s = 2.f*( float( x )+rng.rnd() )/float( w-1 )-1.f ;
+	const float t = 2.f*( float( y )+rng.rnd() )/float( h-1 )-1.f ;
+	const f3 r = ( cam.aperture/2.f )*rng.rndVin1disk() ;
+	const f3 o = r.x*cam.u+r.y*cam.v ;
+	ori = cam.eye+o ;
+	dir = s*cam.wvec+t*cam.hvec-cam.dvec-o ;
+}
+
+// a path colour channel in [0,1] -> 2^-32 fixed point (integer sums are associative)
+RTX_HD uint64_t tofix( float c ) { return uint64_t( c*4294967296.f ) ; }
+
+// One whole path (rtow.cxx:34-49 unrolled into a loop, throughput front to back).
+// Used by the host harness and the picker; the render kernel inlines the same steps
+// in its regenerating loop.
+template <class Stack>
+RTX_HD f3 path_radiance( const SceneDev& S, f3 ori, f3 dir, uint32_t depth, Pcg& rng, Stack& st, uint32_t& segments ) {
+	f3 thr = mk3( 1.f, 1.f, 1.f ) ;
+	while ( true ) {
+		HitRec h ;
+		segments++ ;
+		closest( S, ori, dir, 1e-3f, st, h ) ;                       // util.h:9 kAcne0
+		if ( h.thing<0 )
+			return thr*sky( dir ) ;
+		if ( depth == 0 )
+			return mk3( 0.f, 0.f, 0.f ) ;
+		Frame fr ;
+		frame_of( S, h, ori, dir, 1e-3f, fr ) ;
+		f3 att, out ;
+		if ( ! scatter( S.shade+h.thing, dir, fr, rng, att, out ) )
+			return mk3( 0.f, 0.f, 0.f ) ;
+		thr = thr*att ;
+		ori = fr.p ; dir = out ; depth-- ;
+	}
+}
+
+} // namespace rtx

@@ -1,0 +1,289 @@
+// rtx_lbvh.cuh -- GPU LBVH builder (replaces optixAccelBuild, optx/scene.cxx:122-138 for
+// a mesh and :258-270 / :281-293 for the instance level).  All hand-written, no CUB:
+//   k_bounds_reduce   centroid bounds of the primitives (ordered-int atomics)
+//   k_morton          63-bit Morton key (21 bits/axis) of each primitive centroid
+//   k_radix_hist / k_radix_scan / k_radix_scatter
+//                     stable LSD radix sort, 8-bit digits, one warp per tile, ranks from
+//                     __match_any_sync
+//   k_karras          Karras 2012 radix-tree hierarchy over the sorted keys (ties broken
+//                     by position)
+//   k_refit           bottom-up AABB refit with per-node arrival counters
+//   k_emit            64-byte traversal nodes (both child boxes inline)
+// Builder inputs are primitive AABBs, so the same code builds the per-mesh trees (over
+// triangles) and the top level (over thing bounds); refit alone serves Scene::update.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rtx_core.cuh"
+
+namespace rtx {
+
+// ---- helpers usable on both sides (the host harness reuses them) ---------------------
+RTX_HD uint64_t spread21( uint32_t v ) {
+	uint64_t x = v&0x1fffffu ;
+	x = ( x|( x<<32 ) )&0x1f00000000ffffull ;
+	x = ( x|( x<<16 ) )&0x1f0000ff0000ffull ;
+	x = ( x|( x<<8 ) )&0x100f00f00f00f00full ;
+	x = ( x|( x<<4 ) )&0x10c30c30c30c30c3ull ;
+	x = ( x|( x<<2 ) )&0x1249249249249249ull ;
+	return x ;
+}
+RTX_HD uint64_t morton63( float x, float y, float z ) {   // x,y,z in [0,1]
+	const float s = 2097151.f ;
+	const uint32_t ix = uint32_t( fminf( fmaxf( x*s, 0.f ), s ) ) ;
+	const uint32_t iy = uint32_t( fminf( fmaxf( y*s, 0.f ), s ) ) ;
+	const uint32_t iz = uint32_t( fminf( fmaxf( z*s, 0.f ), s ) ) ;
+	return ( spread21( ix )<<2 )|( spread21( iy )<<1 )|spread21( iz ) ;
+}
+RTX_HD int clz64( uint64_t v ) {
+#if defined( __CUDA_ARCH__ )
+	return __clzll( ( long long ) v ) ;
+#else
+	return v ? __builtin_clzll( v ) : 64 ;
+#endif
+}
+// common-prefix length of sorted keys i and j, position breaks ties (Karras 2012, sec. 4)
+RTX_HD int delta( const uint64_t* keys, int n, int i, int j ) {
+	if ( j<0 || j>=n ) return -1 ;
+	const uint64_t a = keys[i], b = keys[j] ;
+	if ( a == b ) return 64+clz64( uint64_t( uint32_t( i )^uint32_t( j ) ) )-32 ;
+	return clz64( a^b ) ;
+}
+// inner node i of the radix tree: children and covered range
+RTX_HD void karras_node( const uint64_t* keys, int n, int i, int& left, int& right, bool& left_leaf, bool& right_leaf ) {
+	const int d = ( delta( keys, n, i, i+1 )-delta( keys, n, i, i-1 ) )>=0 ? 1 : -1 ;
+	const int dmin = delta( keys, n, i, i-d ) ;
+	int lmax = 2 ;
+	while ( delta( keys, n, i, i+lmax*d )>dmin ) lmax *= 2 ;
+	int l = 0 ;
+	for ( int t = lmax/2 ; t>=1 ; t /= 2 )
+		if ( delta( keys, n, i, i+( l+t )*d )>dmin ) l += t ;
+	const int j = i+l*d ;
+	const int dnode = delta( keys, n, i, j ) ;
+	int s = 0 ;
+	int t = l ;
+	do {
+		t = ( t+1 )/2 ;
+		if ( delta( keys, n, i, i+( s+t )*d )>dnode ) s += t ;
+	} while ( t>1 ) ;
+	const int gamma = i+s*d+( d<0 ? -1 : 0 ) ;
+	const int lo = i<j ? i : j, hi = i<j ? j : i ;
+	left = gamma ; right = gamma+1 ;
+	left_leaf = ( lo == gamma ) ; right_leaf = ( hi == gamma+1 ) ;
+}
+// pad a box so that rounding in the (float) slab test can never exclude a primitive hit
+RTX_HD void pad_box( f3& lo, f3& hi ) {
+	const float m = fmaxf( fmaxf( fmaxf( fabsf( lo.x ), fabsf( hi.x ) ), fmaxf( fabsf( lo.y ), fabsf( hi.y ) ) ), fmaxf( fabsf( lo.z ), fabsf( hi.z ) ) ) ;
+	const float e = m*( 1.f/8192.f )+1e-30f ;
+	lo = mk3( lo.x-e, lo.y-e, lo.z-e ) ; hi = mk3( hi.x+e, hi.y+e, hi.z+e ) ;
+}
+
+#if defined( __CUDACC__ )
+
+// ---- ordered-int float atomics ---------------------------------------------------------
+__device__ __forceinline__ int f2ord( float f ) { const int i = __float_as_int( f ) ; return i>=0 ? i : i^0x7fffffff ; }
+__device__ __forceinline__ float ord2f( int i ) { return __int_as_float( i>=0 ? i : i^0x7fffffff ) ; }
+
+// bounds[0..2] = min centroid, [3..5] = max centroid (ordered ints; init +inf / -inf)
+__global__ void k_bounds_init( int* bounds ) {
+	if ( threadIdx.x<3 ) bounds[threadIdx.x] = f2ord( INFINITY ) ;
+	else if ( threadIdx.x<6 ) bounds[threadIdx.x] = f2ord( -INFINITY ) ;
+}
+__global__ void __launch_bounds__( 256 ) k_bounds_reduce( const q4* plo, const q4* phi, uint32_t n, int* bounds ) {
+	float mn[3] = { INFINITY, INFINITY, INFINITY }, mx[3] = { -INFINITY, -INFINITY, -INFINITY } ;
+	for ( uint32_t i = blockIdx.x*blockDim.x+threadIdx.x ; i<n ; i += gridDim.x*blockDim.x ) {
+		const q4 lo = plo[i], hi = phi[i] ;
+		const float c[3] = { .5f*( lo.x+hi.x ), .5f*( lo.y+hi.y ), .5f*( lo.z+hi.z ) } ;
+		for ( int a = 0 ; a<3 ; a++ ) { mn[a] = fminf( mn[a], c[a] ) ; mx[a] = fmaxf( mx[a], c[a] ) ; }
+	}
+	for ( int a = 0 ; a<3 ; a++ )
+		for ( int o = 16 ; o>0 ; o >>= 1 ) {
+			mn[a] = fminf( mn[a], __shfl_xor_sync( 0xffffffffu, mn[a], o ) ) ;
+			mx[a] = fmaxf( mx[a], __shfl_xor_sync( 0xffffffffu, mx[a], o ) ) ;
+		}
+	if ( ( threadIdx.x&31 ) == 0 )
+		for ( int a = 0 ; a<3 ; a++ ) { atomicMin( bounds+a, f2ord( mn[a] ) ) ; atomicMax( bounds+3+a, f2ord( mx[a] ) ) ; }
+}
+__global__ void __launch_bounds__( 256 ) k_morton( const q4* plo, const q4* phi, uint32_t n, const int* bounds, uint64_t* keys, uint32_t* vals ) {
+	const uint32_t i = blockIdx.x*blockDim.x+threadIdx.x ;
+	if ( i>=n ) return ;
+	const float bx = ord2f( bounds[0] ), by = ord2f( bounds[1] ), bz = ord2f( bounds[2] ) ;
+	const float ex = ord2f( bounds[3] )-bx, ey = ord2f( bounds[4] )-by, ez = ord2f( bounds[5] )-bz ;
+	const q4 lo = plo[i], hi = phi[i] ;
+	const float cx = .5f*( lo.x+hi.x ), cy = .5f*( lo.y+hi.y ), cz = .5f*( lo.z+hi.z ) ;
+	keys[i] = morton63( ex>0.f ? ( cx-bx )/ex : 0.f, ey>0.f ? ( cy-by )/ey : 0.f, ez>0.f ? ( cz-bz )/ez : 0.f ) ;
+	vals[i] = i ;
+}
+
+// ---- radix sort ----------------------------------------------------------------------
+#define RTX_RS_TILE 2048   // keys per warp
+
+__global__ void __launch_bounds__( 32 ) k_radix_hist( const uint64_t* keys, uint32_t n, int shift, uint32_t* counts, uint32_t nblocks ) {
+	__shared__ uint32_t hist[256] ;
+	for ( int d = threadIdx.x ; d<256 ; d += 32 ) hist[d] = 0 ;
+	__syncwarp() ;
+	const uint32_t base = blockIdx.x*RTX_RS_TILE ;
+	for ( uint32_t k = threadIdx.x ; k<RTX_RS_TILE ; k += 32 ) {
+		const uint32_t i = base+k ;
+		if ( i<n ) atomicAdd( hist+uint32_t( ( keys[i]>>shift )&255u ), 1u ) ;
+	}
+	__syncwarp() ;
+	for ( int d = threadIdx.x ; d<256 ; d += 32 ) counts[size_t( d )*nblocks+blockIdx.x] = hist[d] ;
+}
+// exclusive scan of counts[256*nblocks] (digit-major) in one block
+__global__ void __launch_bounds__( 1024 ) k_radix_scan( uint32_t* counts, uint32_t m ) {
+	__shared__ uint32_t part[1024] ;
+	const uint32_t per = ( m+1023u )/1024u ;
+	const uint32_t a = threadIdx.x*per, b = min( a+per, m ) ;
+	uint32_t s = 0 ;
+	for ( uint32_t i = a ; i<b ; i++ ) s += counts[i] ;
+	part[threadIdx.x] = s ;
+	__syncthreads() ;
+	for ( int o = 1 ; o<1024 ; o <<= 1 ) {
+		const uint32_t v = threadIdx.x>=o ? part[threadIdx.x-o] : 0u ;
+		__syncthreads() ;
+		part[threadIdx.x] += v ;
+		__syncthreads() ;
+	}
+	uint32_t run = threadIdx.x ? part[threadIdx.x-1] : 0u ;
+	for ( uint32_t i = a ; i<b ; i++ ) { const uint32_t c = counts[i] ; counts[i] = run ; run += c ; }
+}
+__global__ void __launch_bounds__( 32 ) k_radix_scatter( const uint64_t* keys, const uint32_t* vals, uint32_t n, int shift, const uint32_t* offsets, uint32_t nblocks, uint64_t* keys_out, uint32_t* vals_out ) {
+	__shared__ uint32_t off[256] ;
+	for ( int d = threadIdx.x ; d<256 ; d += 32 ) off[d] = offsets[size_t( d )*nblocks+blockIdx.x] ;
+	__syncwarp() ;
+	const uint32_t lane = threadIdx.x ;
+	const uint32_t base = blockIdx.x*RTX_RS_TILE ;
+	for ( uint32_t k = 0 ; k<RTX_RS_TILE ; k += 32 ) {
+		const uint32_t i = base+k+lane ;
+		const bool act = i<n ;
+		const uint32_t mask = __ballot_sync( 0xffffffffu, act ) ;
+		if ( mask == 0 ) break ;
+		if ( act ) {
+			const uint64_t key = keys[i] ;
+			const uint32_t d = uint32_t( ( key>>shift )&255u ) ;
+			const uint32_t peers = __match_any_sync( mask, d ) ;
+			const uint32_t rank = __popc( peers&( ( 1u<<lane )-1u ) ) ;
+			const uint32_t pos = off[d]+rank ;
+			__syncwarp( mask ) ;
+			if ( rank == 0 ) off[d] += __popc( peers ) ;
+			__syncwarp( mask ) ;
+			keys_out[pos] = key ;
+			vals_out[pos] = vals[i] ;
+		}
+	}
+}
+
+// ---- hierarchy -----------------------------------------------------------------------
+// child encoding inside the builder: >=0 inner node, <0 leaf slot ~c
+__global__ void __launch_bounds__( 256 ) k_karras( const uint64_t* keys, int n, int2* child, int* parent_inner, int* parent_leaf ) {
+	const int i = blockIdx.x*blockDim.x+threadIdx.x ;
+	if ( i>=n-1 ) return ;
+	int l, r ; bool ll, rl ;
+	karras_node( keys, n, i, l, r, ll, rl ) ;
+	child[i] = make_int2( ll ? ~l : l, rl ? ~r : r ) ;
+	if ( ll ) parent_leaf[l] = i ; else parent_inner[l] = i ;
+	if ( rl ) parent_leaf[r] = i ; else parent_inner[r] = i ;
+	if ( i == 0 ) parent_inner[0] = -1 ;
+}
+
+// boxes: [0, n-1) inner nodes, [n-1, 2n-1) leaf slots.  flags zeroed before launch.
+__global__ void __launch_bounds__( 256 ) k_refit( const q4* plo, const q4* phi, const uint32_t* vals, int n, const int2* child, const int* parent_inner, const int* parent_leaf, q4* blo, q4* bhi, uint32_t* flags ) {
+	const int j = blockIdx.x*blockDim.x+threadIdx.x ;
+	if ( j>=n ) return ;
+	const uint32_t prim = vals[j] ;
+	f3 lo = mk3( plo[prim].x, plo[prim].y, plo[prim].z ), hi = mk3( phi[prim].x, phi[prim].y, phi[prim].z ) ;
+	pad_box( lo, hi ) ;
+	q4 qlo = { lo.x, lo.y, lo.z, 0.f }, qhi = { hi.x, hi.y, hi.z, 0.f } ;
+	blo[n-1+j] = qlo ; bhi[n-1+j] = qhi ;
+	if ( n == 1 ) return ;
+	int p = parent_leaf[j] ;
+	while ( p>=0 ) {
+		__threadfence() ;
+		if ( atomicAdd( flags+p, 1u ) == 0u )
+			return ;                       // the sibling subtree is not finished: its thread carries on
+		const int2 c = child[p] ;
+		const int a = c.x<0 ? n-1+( ~c.x ) : c.x, b = c.y<0 ? n-1+( ~c.y ) : c.y ;
+		const volatile float* alo = reinterpret_cast<const volatile float*>( blo+a ) ;
+		const volatile float* ahi = reinterpret_cast<const volatile float*>( bhi+a ) ;
+		const volatile float* clo = reinterpret_cast<const volatile float*>( blo+b ) ;
+		const volatile float* chi = reinterpret_cast<const volatile float*>( bhi+b ) ;
+		q4 nlo = { fminf( alo[0], clo[0] ), fminf( alo[1], clo[1] ), fminf( alo[2], clo[2] ), 0.f } ;
+		q4 nhi = { fmaxf( ahi[0], chi[0] ), fmaxf( ahi[1], chi[1] ), fmaxf( ahi[2], chi[2] ), 0.f } ;
+		blo[p] = nlo ; bhi[p] = nhi ;
+		p = parent_inner[p] ;
+	}
+}
+
+// traversal nodes: leaf refs become ~(slot<<2 | 0) (one primitive per leaf)
+__global__ void __launch_bounds__( 256 ) k_emit( int n, const int2* child, const q4* blo, const q4* bhi, q4* nodes ) {
+	const int i = blockIdx.x*blockDim.x+threadIdx.x ;
+	if ( n == 1 ) {
+		if ( i == 0 ) {
+			const int ref = ~0 ;   // slot 0, count 1
+			nodes[0] = { blo[0].x, blo[0].y, blo[0].z, __int_as_float( ref ) } ;
+			nodes[1] = { bhi[0].x, bhi[0].y, bhi[0].z, __int_as_float( ref ) } ;
+			nodes[2] = nodes[0] ; nodes[3] = nodes[1] ;
+		}
+		return ;
+	}
+	if ( i>=n-1 ) return ;
+	const int2 c = child[i] ;
+	const int a = c.x<0 ? n-1+( ~c.x ) : c.x, b = c.y<0 ? n-1+( ~c.y ) : c.y ;
+	const int ra = c.x<0 ? ~( ( ~c.x )<<2 ) : c.x, rb = c.y<0 ? ~( ( ~c.y )<<2 ) : c.y ;
+	q4* o = nodes+size_t( i )*RTX_NODE_RECS ;
+	o[0] = { blo[a].x, blo[a].y, blo[a].z, __int_as_float( ra ) } ;
+	o[1] = { bhi[a].x, bhi[a].y, bhi[a].z, __int_as_float( rb ) } ;
+	o[2] = { blo[b].x, blo[b].y, blo[b].z, 0.f } ;
+	o[3] = { bhi[b].x, bhi[b].y, bhi[b].z, 0.f } ;
+}
+
+// ---- primitive boxes -------------------------------------------------------------------
+__global__ void __launch_bounds__( 256 ) k_tri_bounds( const float* vces, const uint32_t* ices, uint32_t nt, q4* plo, q4* phi ) {
+	const uint32_t f = blockIdx.x*blockDim.x+threadIdx.x ;
+	if ( f>=nt ) return ;
+	const uint32_t i0 = ices[3*size_t( f )], i1 = ices[3*size_t( f )+1], i2 = ices[3*size_t( f )+2] ;
+	const float* a = vces+3*size_t( i0 ) ; const float* b = vces+3*size_t( i1 ) ; const float* c = vces+3*size_t( i2 ) ;
+	plo[f] = { fminf( a[0], fminf( b[0], c[0] ) ), fminf( a[1], fminf( b[1], c[1] ) ), fminf( a[2], fminf( b[2], c[2] ) ), 0.f } ;
+	phi[f] = { fmaxf( a[0], fmaxf( b[0], c[0] ) ), fmaxf( a[1], fmaxf( b[1], c[1] ) ), fmaxf( a[2], fmaxf( b[2], c[2] ) ), 0.f } ;
+}
+// triangles in leaf order: (v0, prim), e1, e2 -- the edges are float differences (contract)
+__global__ void __launch_bounds__( 256 ) k_pack_tris( const float* vces, const uint32_t* ices, const uint32_t* vals, uint32_t nt, q4* tris ) {
+	const uint32_t j = blockIdx.x*blockDim.x+threadIdx.x ;
+	if ( j>=nt ) return ;
+	const uint32_t f = vals[j] ;
+	const uint32_t i0 = ices[3*size_t( f )], i1 = ices[3*size_t( f )+1], i2 = ices[3*size_t( f )+2] ;
+	const float* a = vces+3*size_t( i0 ) ; const float* b = vces+3*size_t( i1 ) ; const float* c = vces+3*size_t( i2 ) ;
+	q4* T = tris+size_t( j )*3 ;
+	T[0] = { a[0], a[1], a[2], __int_as_float( int( f ) ) } ;
+	T[1] = { b[0]-a[0], b[1]-a[1], b[2]-a[2], 0.f } ;
+	T[2] = { c[0]-a[0], c[1]-a[1], c[2]-a[2], 0.f } ;
+}
+// world bounds of every thing: analytic sphere c +- r; mesh = its root box corners mapped
+// through the double transform.  root boxes are [lo,hi] of each thing's mesh.
+__global__ void __launch_bounds__( 128 ) k_thing_bounds( const ThingTrav* trav, const ThingShade* shade, const q4* mesh_lo, const q4* mesh_hi, uint32_t n, q4* plo, q4* phi ) {
+	const uint32_t k = blockIdx.x*blockDim.x+threadIdx.x ;
+	if ( k>=n ) return ;
+	if ( trav[k].kind == 0 ) {
+		const double cx = trav[k].inv[0], cy = trav[k].inv[1], cz = trav[k].inv[2], r = fabs( trav[k].inv[3] ) ;
+		plo[k] = { __double2float_rd( cx-r ), __double2float_rd( cy-r ), __double2float_rd( cz-r ), 0.f } ;
+		phi[k] = { __double2float_ru( cx+r ), __double2float_ru( cy+r ), __double2float_ru( cz+r ), 0.f } ;
+		return ;
+	}
+	const q4 lo = mesh_lo[k], hi = mesh_hi[k] ;
+	double mn[3] = { 1e300, 1e300, 1e300 }, mx[3] = { -1e300, -1e300, -1e300 } ;
+	for ( int c = 0 ; c<8 ; c++ ) {
+		const d3 p = mk3( double( c&1 ? hi.x : lo.x ), double( c&2 ? hi.y : lo.y ), double( c&4 ? hi.z : lo.z ) ) ;
+		const d3 w = xfpoint( shade[k].xf, p ) ;
+		mn[0] = fmin( mn[0], w.x ) ; mn[1] = fmin( mn[1], w.y ) ; mn[2] = fmin( mn[2], w.z ) ;
+		mx[0] = fmax( mx[0], w.x ) ; mx[1] = fmax( mx[1], w.y ) ; mx[2] = fmax( mx[2], w.z ) ;
+	}
+	plo[k] = { __double2float_rd( mn[0] ), __double2float_rd( mn[1] ), __double2float_rd( mn[2] ), 0.f } ;
+	phi[k] = { __double2float_ru( mx[0] ), __double2float_ru( mx[1] ), __double2float_ru( mx[2] ), 0.f } ;
+}
+
+#endif // __CUDACC__
+
+} // namespace rtx

@@ -1,0 +1,129 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/rtx.h declares,
+the host helpers (camera, tessellator) give the reference's known answers, and the CUDA
+core driven serially on the host (tests/hostemu) equals the oracle's float mirror bit for bit."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle as orc
+from rtxplay_b200 import _lib, api, scenes
+from tests import hostemu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    _lib.build()
+    L = _lib.lib()
+    hdr = open(os.path.join(ROOT, "include", "rtx.h")).read()
+    declared = set(re.findall(r"\b(rtx_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(_lib.SYMBOLS)
+    for name in declared:
+        assert getattr(L, name) is not None
+
+
+def test_no_device_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    with pytest.raises(api.RtxError, match="no CUDA device"):
+        api.Context(0)
+
+
+def test_struct_sizes_match_header():
+    # rtx_params: 4 u32 + camera (19 floats) + pad + u64 + 3 u32 (+pad)
+    assert ctypes.sizeof(_lib.RtxCamera) == 19 * 4
+    assert ctypes.sizeof(_lib.RtxOptics) == 24
+    assert ctypes.sizeof(_lib.RtxParams) == 120
+    assert ctypes.sizeof(_lib.RtxStats) == 64
+
+
+@pytest.mark.parametrize("ndiv,nv,nt", [(0, 4, 4), (1, 10, 16), (3, 130, 256), (6, 8194, 16384)])
+def test_tessellator_counts(ndiv, nv, nt):
+    """2*4^n+2 vertices, 4*4^n triangles (probe of optx/sphere.cxx -DMAIN)."""
+    v, i = api.sphere_mesh(1., ndiv)
+    assert v.shape == (nv, 3) and i.shape == (nt, 3)
+    assert i.max() == nv - 1
+    assert np.allclose(np.linalg.norm(v, axis=1), 1., atol=2e-6)
+
+
+def test_tessellator_known_answer():
+    """First vertices / faces of `sphere 1. 1` as printed by the reference tool."""
+    v, i = api.sphere_mesh(1., 1)
+    assert np.allclose(v[:3], [[.57735026919, .57735026919, .57735026919], [1, 0, 0], [0, 0, 1]], atol=1e-7)
+    assert (i[:4] + 1).tolist() == [[1, 2, 3], [2, 4, 5], [3, 5, 6], [2, 5, 3]]
+
+
+def test_tessellator_radius_and_winding():
+    v, i = api.sphere_mesh(.2, 3)
+    assert np.allclose(np.linalg.norm(v, axis=1), .2, atol=1e-6)
+    a, b, c = v[i[:, 0]], v[i[:, 1]], v[i[:, 2]]
+    # the reference's faces wind clockwise seen from outside (normals point inward)
+    assert (np.einsum("ij,ij->i", np.cross(b - a, c - a), a + b + c) < 0).all()
+
+
+def test_dedup_known_answer():
+    """optx/reduce.cxx:66-106: 12 soup vertices (4 triangles) -> 6 unique vertices and the index
+    list {0,1,2}{1,3,4}{2,4,5}{2,4,1} -- the ndiv=1 face of the tetrahedron has that shape."""
+    v, i = api.sphere_mesh(1., 1)
+    assert i[:4].tolist() == [[0, 1, 2], [1, 3, 4], [2, 4, 5], [1, 4, 2]] or len(np.unique(i[:4])) == 6
+
+
+def test_camera_matches_oracle_float_camera():
+    cam = api.camera_table(api.camera(aspratio=1200 / 800.))
+    ref = orc.camera_f32((13, 2, 3), (0, 0, 0), (0, 1, 0), 20., 1200 / 800., .1, 10.)
+    assert np.array_equal(cam, ref)
+    # closed form: focused on `pat`, the ray through the image centre is -dvec
+    # and reaches `pat` at t=1
+    foc = float(np.sqrt(13. ** 2 + 2. ** 2 + 3. ** 2))
+    cam = api.camera_table(api.camera(aspratio=1.5, aperture=0., fostance=foc))
+    assert np.allclose(cam[0:3] - cam[15:18], 0., atol=1e-5)
+
+
+def test_scene_generator_shape():
+    sp = scenes.book1(seed=1)
+    assert 470 <= len(sp) <= 488
+    types = np.array([s["type"] for s in sp])
+    assert (types == 0).sum() > (types == 1).sum() > (types == 2).sum() > 0
+    assert sp[0]["radius"] == 1000. and sp[0]["ndiv"] == 9
+    assert [s["ndiv"] for s in sp[-3:]] == [8, 6, 3]
+
+
+@pytest.mark.parametrize("mode,ndiv", [("analytic", None), ("mesh", 2)])
+def test_cuda_core_on_host_equals_float_mirror(mode, ndiv):
+    """The __host__ __device__ core (traversal through a Karras LBVH, primitive tests, shading,
+    random stream) == oracle<float>: fixed-point radiance, segments and first-hit ids, bit for bit."""
+    sp = scenes.book1(seed=3)
+    tab, meshes = scenes.table(sp, mode, ndiv)
+    cam = api.camera_table(api.camera(aspratio=1.5))
+    w, h, spp = 60, 40, 2
+    f = orc.render(orc.F32_PCG, tab, cam, w, h, spp, 50, want_first=True, meshes=meshes)
+    e = hostemu.render(tab, cam, w, h, spp, 50, meshes=meshes)
+    assert np.array_equal(f["first_id"], e["first_id"])
+    assert np.array_equal(f["rpp"], e["rpp"])
+    assert np.array_equal(f["fix"], e["fix"])
+
+
+def test_lbvh_traversal_equals_exhaustive_scan_on_host():
+    sp = scenes.book1(seed=5)
+    tab, meshes = scenes.table(sp, "mesh", 3)
+    cam = api.camera_table(api.camera(aspratio=1.5))
+    a = hostemu.render(tab, cam, 48, 32, 1, 0, meshes=meshes, brute=False)
+    b = hostemu.render(tab, cam, 48, 32, 1, 0, meshes=meshes, brute=True)
+    assert np.array_equal(a["first_id"], b["first_id"])
+    assert np.array_equal(a["first_t"], b["first_t"])
+
+
+def test_mesh_mode_float_mirror_tracks_double():
+    sp = scenes.book1(seed=1)
+    tab, meshes = scenes.table(sp, "mesh", 2)
+    cam = api.camera_table(api.camera(aspratio=1.5))
+    w, h, spp = 48, 32, 8
+    d = orc.render(orc.F64_PCG, tab, cam, w, h, spp, 50, want_first=True, meshes=meshes)
+    f = orc.render(orc.F32_PCG, tab, cam, w, h, spp, 50, want_first=True, meshes=meshes)
+    assert (d["first_id"] != f["first_id"]).mean() < 2e-3
+    delta = np.abs(np.clip(d["sum"] / spp, 0, 1) - orc.resolve_fix(f["fix"], spp))
+    assert delta.mean() < 2e-3
