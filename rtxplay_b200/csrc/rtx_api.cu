@@ -31,16 +31,22 @@ thread_local std::string g_init_error ;
 	char b_[512] ; snprintf( b_, sizeof( b_ ), "CUDA call (%s) failed with error '%s' (%s:%d)", #call, cudaGetErrorString( e_ ), __FILE__, __LINE__ ) ; \
 	throw std::runtime_error( b_ ) ; } } while ( 0 )
 
-struct Lbvh {           // one built tree and, when kept, what a refit needs
+struct Lbvh {           // one built tree: wide traversal nodes + (when kept) the binary tree a refit needs
 	uint32_t  n = 0 ;
+	uint32_t  n_nodes = 0 ;       // wide nodes in use
+	uint32_t  cap_nodes = 0 ;     // wide nodes allocated
 	q4*       nodes = nullptr ;
 	uint32_t* order = nullptr ;   // leaf slot -> primitive
-	int2*     child = nullptr ;
+	int2*     child = nullptr ;   // binary tree (Karras)
+	int2*     range = nullptr ;
 	int*      parent_inner = nullptr ;
 	int*      parent_leaf = nullptr ;
 	q4*       blo = nullptr ;
 	q4*       bhi = nullptr ;
 	uint32_t* flags = nullptr ;
+	int2*     front0 = nullptr ;  // collapse frontiers
+	int2*     front1 = nullptr ;
+	uint32_t* counters = nullptr ;
 	q4        root_lo = { 0, 0, 0, 0 }, root_hi = { 0, 0, 0, 0 } ;
 } ;
 
@@ -93,6 +99,9 @@ struct rtx_ctx {
 	float*    d_albedos = nullptr ;
 	uint32_t* d_pick = nullptr ;
 	unsigned long long* d_counter = nullptr ;
+	uint32_t* d_tile_counter = nullptr ;
+	int32_t*  d_ovf = nullptr ;      // overflow stacks of the resident render warps
+	uint32_t  render_grid = 0 ;
 
 	// statistics
 	uint64_t bytes = 0 ;
@@ -114,44 +123,77 @@ template <class T> void dfree( rtx_ctx* c, T*& p, size_t n ) {
 	if ( p ) { cudaFree( p ) ; c->bytes -= ( n ? n : 1 )*sizeof( T ) ; p = nullptr ; }
 }
 
-void lbvh_free( rtx_ctx* c, Lbvh& b ) {
+void lbvh_free_binary( rtx_ctx* c, Lbvh& b ) {
 	const size_t n = b.n ;
-	dfree( c, b.nodes, ( n>1 ? n-1 : 1 )*RTX_NODE_RECS ) ;
-	dfree( c, b.order, n ) ;
 	dfree( c, b.child, n>1 ? n-1 : 1 ) ;
+	dfree( c, b.range, n>1 ? n-1 : 1 ) ;
 	dfree( c, b.parent_inner, n>1 ? n-1 : 1 ) ;
 	dfree( c, b.parent_leaf, n ) ;
 	dfree( c, b.blo, 2*n ) ;
 	dfree( c, b.bhi, 2*n ) ;
 	dfree( c, b.flags, n>1 ? n-1 : 1 ) ;
-	b.n = 0 ;
+	dfree( c, b.front0, n ) ;
+	dfree( c, b.front1, n ) ;
+	dfree( c, b.counters, 2 ) ;
 }
 
-// bottom-up boxes + traversal nodes for an existing topology
-void lbvh_refit( rtx_ctx* c, Lbvh& b, const q4* plo, const q4* phi ) {
+void lbvh_free( rtx_ctx* c, Lbvh& b ) {
+	lbvh_free_binary( c, b ) ;
+	dfree( c, b.nodes, size_t( b.cap_nodes )*RTX_NODE_RECS ) ;
+	dfree( c, b.order, b.n ) ;
+	b.n = 0 ; b.n_nodes = 0 ; b.cap_nodes = 0 ;
+}
+
+// bottom-up boxes of the binary tree, then its collapse into wide traversal nodes, level
+// by level (the host reads back the size of each next frontier)
+void lbvh_refit( rtx_ctx* c, Lbvh& b, const q4* plo, const q4* phi, int leaf_max ) {
 	const int n = int( b.n ) ;
 	CK( cudaMemsetAsync( b.flags, 0, sizeof( uint32_t )*( n>1 ? n-1 : 1 ), c->stream ) ) ;
 	k_refit<<<( n+255 )/256, 256, 0, c->stream>>>( plo, phi, b.order, n, b.child, b.parent_inner, b.parent_leaf, b.blo, b.bhi, b.flags ) ;
-	k_emit<<<( n+255 )/256, 256, 0, c->stream>>>( n, b.child, b.blo, b.bhi, b.nodes ) ;
-	c->launches += 2 ;
+	c->launches += 1 ;
 	CK( cudaGetLastError() ) ;
+	const int2 root = make_int2( 0, 0 ) ;
+	uint32_t counters[2] = { 1u, 0u } ;   // wide node 0 is the root
+	CK( cudaMemcpyAsync( b.front0, &root, sizeof( int2 ), cudaMemcpyHostToDevice, c->stream ) ) ;
+	uint32_t n_front = 1 ;
+	int2* fin = b.front0 ; int2* fout = b.front1 ;
+	while ( n_front ) {
+		counters[1] = 0 ;
+		CK( cudaMemcpyAsync( b.counters, counters, sizeof( counters ), cudaMemcpyHostToDevice, c->stream ) ) ;
+		k_wide_level<<<( n_front+127 )/128, 128, 0, c->stream>>>( fin, n_front, n, leaf_max, b.child, b.range, b.blo, b.bhi, b.nodes, fout, b.counters ) ;
+		c->launches += 1 ;
+		CK( cudaGetLastError() ) ;
+		CK( cudaMemcpyAsync( counters, b.counters, sizeof( counters ), cudaMemcpyDeviceToHost, c->stream ) ) ;
+		CK( cudaStreamSynchronize( c->stream ) ) ;
+		n_front = counters[1] ;
+		std::swap( fin, fout ) ;
+	}
+	b.n_nodes = counters[0] ;
 	CK( cudaMemcpyAsync( &b.root_lo, b.blo, sizeof( q4 ), cudaMemcpyDeviceToHost, c->stream ) ) ;
 	CK( cudaMemcpyAsync( &b.root_hi, b.bhi, sizeof( q4 ), cudaMemcpyDeviceToHost, c->stream ) ) ;
 	CK( cudaStreamSynchronize( c->stream ) ) ;
 }
 
-// Morton keys -> radix sort -> Karras hierarchy -> refit -> nodes
-void lbvh_build( rtx_ctx* c, Lbvh& b, const q4* plo, const q4* phi, uint32_t n ) {
+// Morton keys -> radix sort -> Karras hierarchy -> refit -> wide nodes
+void lbvh_build( rtx_ctx* c, Lbvh& b, const q4* plo, const q4* phi, uint32_t n, int leaf_max, bool keep_binary ) {
 	lbvh_free( c, b ) ;
 	b.n = n ;
-	b.nodes        = dalloc<q4>( c, size_t( n>1 ? n-1 : 1 )*RTX_NODE_RECS ) ;
+	// a wide node replaces a binary inner node covering more than leaf_max primitives (or the
+	// root): there are fewer than n/leaf_max+1 ... n-1 of those; allocate the safe bound,
+	// shrink after the build
+	b.cap_nodes    = n>1 ? n-1 : 1 ;
+	b.nodes        = dalloc<q4>( c, size_t( b.cap_nodes )*RTX_NODE_RECS ) ;
 	b.order        = dalloc<uint32_t>( c, n ) ;
 	b.child        = dalloc<int2>( c, n>1 ? n-1 : 1 ) ;
+	b.range        = dalloc<int2>( c, n>1 ? n-1 : 1 ) ;
 	b.parent_inner = dalloc<int>( c, n>1 ? n-1 : 1 ) ;
 	b.parent_leaf  = dalloc<int>( c, n ) ;
 	b.blo          = dalloc<q4>( c, 2*size_t( n ) ) ;
 	b.bhi          = dalloc<q4>( c, 2*size_t( n ) ) ;
 	b.flags        = dalloc<uint32_t>( c, n>1 ? n-1 : 1 ) ;
+	b.front0       = dalloc<int2>( c, n ) ;
+	b.front1       = dalloc<int2>( c, n ) ;
+	b.counters     = dalloc<uint32_t>( c, 2 ) ;
 
 	const uint32_t nblocks = ( n+RTX_RS_TILE-1 )/RTX_RS_TILE ;
 	int* bounds = dalloc<int>( c, 6 ) ;
@@ -175,13 +217,24 @@ void lbvh_build( rtx_ctx* c, Lbvh& b, const q4* plo, const q4* phi, uint32_t n )
 	}
 	// 8 passes: the sorted data is back in keys0 / b.order
 	if ( n>1 ) {
-		k_karras<<<( n-1+255 )/256, 256, 0, c->stream>>>( keys0, int( n ), b.child, b.parent_inner, b.parent_leaf ) ;
+		k_karras<<<( n-1+255 )/256, 256, 0, c->stream>>>( keys0, int( n ), b.child, b.range, b.parent_inner, b.parent_leaf ) ;
 		c->launches += 1 ;
 	}
 	CK( cudaGetLastError() ) ;
-	lbvh_refit( c, b, plo, phi ) ;
+	lbvh_refit( c, b, plo, phi, leaf_max ) ;
 
 	dfree( c, bounds, 6 ) ; dfree( c, keys0, n ) ; dfree( c, keys1, n ) ; dfree( c, vals1, n ) ; dfree( c, counts, size_t( 256 )*nblocks ) ;
+	if ( ! keep_binary ) {
+		// a mesh is never refitted: drop the binary tree and trim the node array
+		lbvh_free_binary( c, b ) ;
+		if ( b.n_nodes<b.cap_nodes ) {
+			q4* trimmed = dalloc<q4>( c, size_t( b.n_nodes )*RTX_NODE_RECS ) ;
+			CK( cudaMemcpyAsync( trimmed, b.nodes, sizeof( q4 )*size_t( b.n_nodes )*RTX_NODE_RECS, cudaMemcpyDeviceToDevice, c->stream ) ) ;
+			CK( cudaStreamSynchronize( c->stream ) ) ;
+			dfree( c, b.nodes, size_t( b.cap_nodes )*RTX_NODE_RECS ) ;
+			b.nodes = trimmed ; b.cap_nodes = b.n_nodes ;
+		}
+	}
 }
 
 // host thing list -> device records + world bounds
@@ -272,7 +325,10 @@ void do_resolve( rtx_ctx* c, uint64_t total_spp ) {
 void do_render( rtx_ctx* c, const rtx_params* p, bool resolve ) {
 	const FrameArgs a = frame_args( c, p ) ;
 	CK( cudaEventRecord( c->ev0, c->stream ) ) ;
-	k_render<<<tile_grid( a.w, a.h ), RTX_BLOCK, 0, c->stream>>>( a ) ;
+	if ( a.depth>255u ) throw std::runtime_error( "rtx: depth above 255 is not supported" ) ;
+	const uint32_t n_tiles = ( ( a.w+7u )>>3 )*( ( a.h+3u )>>2 ) ;
+	CK( cudaMemsetAsync( c->d_tile_counter, 0, sizeof( uint32_t ), c->stream ) ) ;
+	k_render<<<min( c->render_grid, n_tiles ), 32, 0, c->stream>>>( a, c->d_tile_counter, c->d_ovf ) ;
 	c->launches += 1 ;
 	CK( cudaGetLastError() ) ;
 	CK( cudaEventRecord( c->ev1, c->stream ) ) ;
@@ -336,6 +392,13 @@ int rtx_init( int device, rtx_ctx** out ) {
 		CK( cudaEventCreate( &c->ev0 ) ) ; CK( cudaEventCreate( &c->ev1 ) ) ;
 		c->d_pick = dalloc<uint32_t>( c, 1 ) ;
 		c->d_counter = dalloc<unsigned long long>( c, 1 ) ;
+		c->d_tile_counter = dalloc<uint32_t>( c, 1 ) ;
+		// the render kernel is persistent: one warp per CTA, as many CTAs as fit
+		int per_sm = 0 ;
+		CK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm, k_render, 32, 0 ) ) ;
+		if ( per_sm<1 ) per_sm = 1 ;
+		c->render_grid = uint32_t( per_sm )*uint32_t( prop.multiProcessorCount ) ;
+		c->d_ovf = dalloc<int32_t>( c, size_t( c->render_grid )*RTX_POOL_R*RTX_POOL_OVF ) ;
 		*out = c ;
 		return 0 ;
 	} catch ( const std::exception& e ) {
@@ -359,7 +422,8 @@ void rtx_shutdown( rtx_ctx* c ) {
 	dfree( c, c->d_tb_lo, c->n_things_dev ) ; dfree( c, c->d_tb_hi, c->n_things_dev ) ;
 	dfree( c, c->d_tp_lo, c->n_things_dev ) ; dfree( c, c->d_tp_hi, c->n_things_dev ) ;
 	free_frame( c ) ;
-	dfree( c, c->d_pick, 1 ) ; dfree( c, c->d_counter, 1 ) ;
+	dfree( c, c->d_pick, 1 ) ; dfree( c, c->d_counter, 1 ) ; dfree( c, c->d_tile_counter, 1 ) ;
+	dfree( c, c->d_ovf, size_t( c->render_grid )*RTX_POOL_R*RTX_POOL_OVF ) ;
 	cudaEventDestroy( c->ev0 ) ; cudaEventDestroy( c->ev1 ) ;
 	cudaStreamDestroy( c->stream ) ;
 	delete c ;
@@ -383,7 +447,7 @@ int rtx_mesh_create( rtx_ctx* c, const float* xyz, uint32_t nv, const uint32_t* 
 	CK( cudaEventRecord( c->ev0, c->stream ) ) ;
 	k_tri_bounds<<<( nt+255 )/256, 256, 0, c->stream>>>( m.vces, m.ices, nt, plo, phi ) ;
 	c->launches += 1 ;
-	lbvh_build( c, m.bvh, plo, phi, nt ) ;
+	lbvh_build( c, m.bvh, plo, phi, nt, RTX_LEAF_MAX, false ) ;
 	k_pack_tris<<<( nt+255 )/256, 256, 0, c->stream>>>( m.vces, m.ices, m.bvh.order, nt, m.tris ) ;
 	c->launches += 1 ;
 	CK( cudaGetLastError() ) ;
@@ -448,7 +512,7 @@ int rtx_accel_build( rtx_ctx* c ) {
 	CK( cudaEventRecord( c->ev0, c->stream ) ) ;
 	upload_things( c ) ;
 	const uint32_t n = c->n_things_dev ;
-	if ( n ) lbvh_build( c, c->tlas, c->d_tp_lo, c->d_tp_hi, n ) ;
+	if ( n ) lbvh_build( c, c->tlas, c->d_tp_lo, c->d_tp_hi, n, 1, true ) ;
 	else     lbvh_free( c, c->tlas ) ;
 	CK( cudaEventRecord( c->ev1, c->stream ) ) ;
 	CK( cudaStreamSynchronize( c->stream ) ) ;
@@ -464,7 +528,7 @@ int rtx_accel_refit( rtx_ctx* c ) {
 		throw std::runtime_error( "rtx_accel_refit: thing count changed since rtx_accel_build" ) ;
 	CK( cudaEventRecord( c->ev0, c->stream ) ) ;
 	upload_things( c ) ;
-	if ( c->tlas.n ) lbvh_refit( c, c->tlas, c->d_tp_lo, c->d_tp_hi ) ;
+	if ( c->tlas.n ) lbvh_refit( c, c->tlas, c->d_tp_lo, c->d_tp_hi, 1 ) ;
 	CK( cudaEventRecord( c->ev1, c->stream ) ) ;
 	CK( cudaStreamSynchronize( c->stream ) ) ;
 	CK( cudaEventElapsedTime( &c->ms_tlas, c->ev0, c->ev1 ) ) ;

@@ -25,8 +25,27 @@
 
 #if defined( __CUDA_ARCH__ )
 #define RTX_LDG( p ) __ldg( p )
+// warp vote: the tracing loops are written warp-synchronously (all 32 lanes stay in the
+// loop until none has work) so that the lanes of a warp reconverge every iteration
+#define RTX_ANY( pred ) __any_sync( 0xffffffffu, ( pred ) )
 #else
 #define RTX_LDG( p ) ( *( p ) )
+#define RTX_ANY( pred ) ( pred )
+#endif
+
+// traversal statistics for the host harness (compiled out of the product)
+#if defined( RTX_STATS )
+namespace rtx { struct Stats { unsigned long long rays, nodes, leaves, tris, things, spheres, enters, pushes, maxsp ; } ; extern Stats g_stats ; }
+#endif
+#if defined( RTX_STATS ) && ! defined( __CUDA_ARCH__ )
+namespace rtx { void trace_event( char c ) ; }
+#define RTX_EVENT( c ) rtx::trace_event( c )
+#define RTX_COUNT( f ) ( rtx::g_stats.f++ )
+#define RTX_COUNT_MAX( f, v ) do { if ( ( unsigned long long )( v )>rtx::g_stats.f ) rtx::g_stats.f = ( v ) ; } while ( 0 )
+#else
+#define RTX_EVENT( c ) ( ( void ) 0 )
+#define RTX_COUNT( f ) ( ( void ) 0 )
+#define RTX_COUNT_MAX( f, v ) ( ( void ) 0 )
 #endif
 
 namespace rtx {
@@ -102,12 +121,20 @@ struct Pcg {
 // ----------------------------------------------------------------------------- scene (device view)
 struct q4 { float x, y, z, w ; } ;   // 16-byte record, bit-compatible with float4
 
-// BVH2 node, 64 bytes = 4 x 16-byte records (vector loads):
-//   r0 = child0.lo.xyz, asfloat(child0 ref)   r1 = child0.hi.xyz, asfloat(child1 ref)
-//   r2 = child1.lo.xyz, -                     r3 = child1.hi.xyz, -
-// child ref >= 0: inner node index; < 0: leaf, ~ref = first<<2 | (count-1)
-#define RTX_NODE_RECS 4
-#define RTX_LEAF_MAX  4
+// Wide (4-ary) BVH node, 128 bytes = 8 x 16-byte records = one cache line, child boxes
+// in SoA form so that each record is one vector load feeding four slab tests:
+//   r0 = lo.x[0..3]  r1 = lo.y[0..3]  r2 = lo.z[0..3]
+//   r3 = hi.x[0..3]  r4 = hi.y[0..3]  r5 = hi.z[0..3]
+//   r6 = child refs[0..3] (bit patterns)   r7 = unused
+// child ref: 0 <= ref < RTX_REF_EMPTY inner node index; ref < 0 leaf, ~ref = first<<3 |
+// (count-1); RTX_REF_EMPTY marks an unused slot.  The two values above it are stack
+// sentinels.
+#define RTX_NODE_RECS  8
+#define RTX_WIDTH      4
+#define RTX_LEAF_MAX   4            // triangles per mesh leaf (top level: 1 thing per leaf)
+#define RTX_REF_EMPTY  0x7ffffffd
+#define RTX_STK_DONE   0x7ffffffe   // bottom of the stack
+#define RTX_STK_RETURN 0x7fffffff   // leave the mesh, back to the top level
 
 // per-thing record read by traversal (128 bytes)
 struct ThingTrav {
@@ -232,30 +259,39 @@ RTX_HD bool better( float t, int32_t thing, int32_t prim, const HitRec& best ) {
 // ----------------------------------------------------------------------------- box test
 // Conservative slab test (boxes are padded at build time, the far bound carries a
 // relative slack): may visit too much, never too little.  This is the one place where
-// FMA is used on purpose.
+// FMA and an approximate reciprocal are used on purpose -- it never decides a result.
 #define RTX_SLACK 1.0000038f
 RTX_HD float safe_rcp( float d ) {
 	const float big = 1e30f ;
-	return fabsf( d )>1e-30f ? 1.f/d : ( d<0.f ? -big : big ) ;   // -0.f counts as +
+#if defined( __CUDA_ARCH__ )
+	return fabsf( d )>1e-30f ? __fdividef( 1.f, d ) : ( d<0.f ? -big : big ) ;   // -0.f counts as +
+#else
+	return fabsf( d )>1e-30f ? 1.f/d : ( d<0.f ? -big : big ) ;
+#endif
 }
-RTX_HD bool slab( const f3& lo, const f3& hi, const f3& idir, const f3& ood, float tmin, float tbest_s, float& tn ) {
-	const float x0 = fmaf( lo.x, idir.x, -ood.x ), x1 = fmaf( hi.x, idir.x, -ood.x ) ;
-	const float y0 = fmaf( lo.y, idir.y, -ood.y ), y1 = fmaf( hi.y, idir.y, -ood.y ) ;
-	const float z0 = fmaf( lo.z, idir.z, -ood.z ), z1 = fmaf( hi.z, idir.z, -ood.z ) ;
-	tn = fmaxf( fmaxf( fminf( x0, x1 ), fminf( y0, y1 ) ), fmaxf( fminf( z0, z1 ), tmin ) ) ;
+// entry distance of the ray into box (lo,hi), or +inf when it misses [tmin, tbest]
+RTX_HD float slab( float lox, float loy, float loz, float hix, float hiy, float hiz, const f3& idir, const f3& ood, float tmin, float tbest_s ) {
+	const float x0 = fmaf( lox, idir.x, -ood.x ), x1 = fmaf( hix, idir.x, -ood.x ) ;
+	const float y0 = fmaf( loy, idir.y, -ood.y ), y1 = fmaf( hiy, idir.y, -ood.y ) ;
+	const float z0 = fmaf( loz, idir.z, -ood.z ), z1 = fmaf( hiz, idir.z, -ood.z ) ;
+	const float tn = fmaxf( fmaxf( fminf( x0, x1 ), fminf( y0, y1 ) ), fmaxf( fminf( z0, z1 ), tmin ) ) ;
 	const float tf = fminf( fminf( fmaxf( x0, x1 ), fmaxf( y0, y1 ) ), fminf( fmaxf( z0, z1 ), tbest_s ) ) ;
-	return tn<=tf*RTX_SLACK ;
+	return tn<=tf*RTX_SLACK ? tn : INFINITY ;
 }
 
 // ----------------------------------------------------------------------------- traversal
-// One stack for both levels: entering a mesh pushes RTX_STK_RETURN, popping it restores
-// the world-space ray.  Stack is a policy: shared memory + overflow on the device.
-#define RTX_STK_RETURN 0x7fffffff
-
+// "while-while" over the 4-wide trees, warp-synchronous: all lanes of the warp first walk
+// inner nodes until none of them holds one (lanes that reached a leaf wait), then every lane
+// with a leaf processes it.  The loops are driven by warp votes instead of per-lane exits:
+// with independent thread scheduling, lanes that leave a loop at different times are not
+// brought back together, and the warp degenerates into small groups executing the same
+// code one after the other (measured: 6.9 of 32 lanes active).  `active` = this lane has
+// a ray; idle lanes tag along.  One stack serves both levels: entering a mesh pushes
+// RTX_STK_RETURN, popping it restores the world-space ray; RTX_STK_DONE sits at the bottom.
 template <class Stack>
-RTX_HD void closest( const SceneDev& S, const f3& o, const f3& d, float tmin, Stack& st, HitRec& best, uint32_t* visits = nullptr ) {
+RTX_HD void closest( const SceneDev& S, const f3& o, const f3& d, float tmin, Stack& st, HitRec& best, bool active = true ) {
 	best.t = INFINITY ; best.thing = -1 ; best.prim = -1 ; best.u = 0.f ; best.v = 0.f ;
-	if ( S.n_things == 0 )
+	if ( S.n_things == 0 )   // uniform over the launch
 		return ;
 	float tbest_s = INFINITY ;
 
@@ -269,31 +305,56 @@ RTX_HD void closest( const SceneDev& S, const f3& o, const f3& d, float tmin, St
 	int32_t thing = -1 ;
 
 	st.reset() ;
-	int32_t cur = 0 ;   // root
+	st.push( RTX_STK_DONE ) ;
+	int32_t cur = active ? 0 : RTX_STK_DONE ;   // 0 = root
+	RTX_COUNT( rays ) ;
 	while ( true ) {
-		if ( cur>=0 && cur != RTX_STK_RETURN ) {
-			// inner node: test both children
-			const q4* n = nodes+size_t( cur )*RTX_NODE_RECS ;
-			const q4 r0 = ldq( n ), r1 = ldq( n+1 ), r2 = ldq( n+2 ), r3 = ldq( n+3 ) ;
-			if ( visits ) ( *visits )++ ;
-			float t0, t1 ;
-			const bool h0 = slab( mk3( r0.x, r0.y, r0.z ), mk3( r1.x, r1.y, r1.z ), idir, ood, tmin, tbest_s, t0 ) ;
-			const bool h1 = slab( mk3( r2.x, r2.y, r2.z ), mk3( r3.x, r3.y, r3.z ), idir, ood, tmin, tbest_s, t1 ) ;
-			const int32_t c0 = asint( r0.w ), c1 = asint( r1.w ) ;
-			if ( h0 && h1 ) {
-				const bool swap = t1<t0 ;
-				cur = swap ? c1 : c0 ;
-				st.push( swap ? c0 : c1 ) ;
-				continue ;
+		// ---- phase 1: inner nodes
+		while ( RTX_ANY( uint32_t( cur )<uint32_t( RTX_REF_EMPTY ) ) ) {
+			if ( uint32_t( cur )<uint32_t( RTX_REF_EMPTY ) ) {
+				const q4* n = nodes+size_t( cur )*RTX_NODE_RECS ;
+				RTX_COUNT( nodes ) ; RTX_EVENT( 'N' ) ;
+				const q4 lx = ldq( n ), ly = ldq( n+1 ), lz = ldq( n+2 ), hx = ldq( n+3 ), hy = ldq( n+4 ), hz = ldq( n+5 ), rf = ldq( n+6 ) ;
+				int32_t c0 = asint( rf.x ), c1 = asint( rf.y ), c2 = asint( rf.z ), c3 = asint( rf.w ) ;
+				float t0 = slab( lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, idir, ood, tmin, tbest_s ) ;
+				float t1 = slab( lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, idir, ood, tmin, tbest_s ) ;
+				float t2 = slab( lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, idir, ood, tmin, tbest_s ) ;
+				float t3 = slab( lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, idir, ood, tmin, tbest_s ) ;
+				if ( c0 == RTX_REF_EMPTY ) t0 = INFINITY ;
+				if ( c1 == RTX_REF_EMPTY ) t1 = INFINITY ;
+				if ( c2 == RTX_REF_EMPTY ) t2 = INFINITY ;
+				if ( c3 == RTX_REF_EMPTY ) t3 = INFINITY ;
+				// sort the four (entry distance, child) pairs, nearest first
+#define RTX_CSWAP( ta, ca, tb, cb ) if ( tb<ta ) { const float tt = ta ; ta = tb ; tb = tt ; const int32_t cc = ca ; ca = cb ; cb = cc ; }
+				RTX_CSWAP( t0, c0, t1, c1 ) RTX_CSWAP( t2, c2, t3, c3 ) RTX_CSWAP( t0, c0, t2, c2 ) RTX_CSWAP( t1, c1, t3, c3 ) RTX_CSWAP( t1, c1, t2, c2 )
+#undef RTX_CSWAP
+				if ( t0 == INFINITY )
+					cur = st.pop() ;
+				else {
+					if ( t3<INFINITY ) st.push( c3 ) ;
+					if ( t2<INFINITY ) st.push( c2 ) ;
+					if ( t1<INFINITY ) st.push( c1 ) ;
+					cur = c0 ;
+				}
 			}
-			if ( h0 ) { cur = c0 ; continue ; }
-			if ( h1 ) { cur = c1 ; continue ; }
-		} else if ( cur<0 ) {
-			// leaf
+		}
+		if ( ! RTX_ANY( cur != RTX_STK_DONE ) )
+			break ;
+		// ---- phase 2: a leaf, or the return to the top level
+		if ( cur == RTX_STK_RETURN ) {
+			idir = mk3( safe_rcp( d.x ), safe_rcp( d.y ), safe_rcp( d.z ) ) ;
+			ood  = mk3( o.x*idir.x, o.y*idir.y, o.z*idir.z ) ;
+			nodes = S.tlas_nodes ; tris = nullptr ; thing = -1 ;
+			cur = st.pop() ;
+			RTX_EVENT( 'R' ) ;
+		} else if ( cur != RTX_STK_DONE ) {
 			const uint32_t ref = uint32_t( ~cur ) ;
-			const uint32_t first = ref>>2, count = ( ref&3u )+1u ;
+			const uint32_t first = ref>>3, count = ( ref&7u )+1u ;
+			cur = RTX_REF_EMPTY ;   // "pop next" unless a mesh is entered
 			if ( tris ) {
+				RTX_COUNT( leaves ) ; RTX_EVENT( char( '0'+count ) ) ;
 				for ( uint32_t k = 0 ; k<count ; k++ ) {
+					RTX_COUNT( tris ) ;
 					const q4* T = tris+size_t( first+k )*3 ;
 					const q4 a = ldq( T ), b = ldq( T+1 ), c = ldq( T+2 ) ;
 					float t, u, v ;
@@ -306,12 +367,14 @@ RTX_HD void closest( const SceneDev& S, const f3& o, const f3& d, float tmin, St
 					}
 				}
 			} else {
-				// top level: count is 1 by construction
+				// top level: one thing per leaf
 				const int32_t k = int32_t( RTX_LDG( S.tlas_order+first ) ) ;
 				const ThingTrav* tt = S.trav+k ;
+				RTX_COUNT( things ) ;
 				const double m0 = RTX_LDG( tt->inv+0 ), m1 = RTX_LDG( tt->inv+1 ), m2 = RTX_LDG( tt->inv+2 ), m3 = RTX_LDG( tt->inv+3 ) ;
 				if ( RTX_LDG( &tt->kind ) == 0 ) {
 					double td ;
+					RTX_COUNT( spheres ) ; RTX_EVENT( 'P' ) ;
 					if ( sphere_root( mk3( m0, m1, m2 ), m3, wide( o ), wide( d ), double( tmin ), td ) ) {
 						const float t = float( td ) ;
 						if ( better( t, k, -1, best ) ) {
@@ -335,18 +398,12 @@ RTX_HD void closest( const SceneDev& S, const f3& o, const f3& d, float tmin, St
 					thing = k ;
 					st.push( RTX_STK_RETURN ) ;
 					cur = 0 ;
-					continue ;
+					RTX_COUNT( enters ) ; RTX_EVENT( 'E' ) ;
 				}
 			}
-		} else {
-			// back to the top level
-			idir = mk3( safe_rcp( d.x ), safe_rcp( d.y ), safe_rcp( d.z ) ) ;
-			ood  = mk3( o.x*idir.x, o.y*idir.y, o.z*idir.z ) ;
-			nodes = S.tlas_nodes ; tris = nullptr ; thing = -1 ;
+			if ( cur == RTX_REF_EMPTY )
+				cur = st.pop() ;
 		}
-		if ( st.empty() )
-			break ;
-		cur = st.pop() ;
 	}
 }
 

@@ -9,6 +9,7 @@
 #include <stdint.h>
 
 #include "rtx_core.cuh"
+#include "rtx_pool.cuh"
 
 namespace rtx {
 
@@ -63,74 +64,116 @@ inline uint32_t tile_grid( uint32_t w, uint32_t h ) {
 	return ( warps*32u+RTX_BLOCK-1u )/RTX_BLOCK ;
 }
 
-// The path tracer.  One lane = one pixel; the lane walks through its samples and starts
-// the next path the moment the current one ends (no lane waits for the longest path of
-// its warp, only for the warp's slowest pixel).  Colour is summed in 2^-32 fixed point.
-__global__ void __launch_bounds__( RTX_BLOCK ) k_render( const FrameArgs a ) {
-	__shared__ int32_t stack_mem[RTX_SM_STACK*RTX_BLOCK] ;
-	uint32_t x, y ;
-	if ( ! tile_pixel( a.w, a.h, x, y ) )
-		return ;
-	const uint32_t pix = a.w*y+x ;
-	DevStack st ;
-	st.base = stack_mem+threadIdx.x ;
-
-	uint64_t acc0 = 0, acc1 = 0, acc2 = 0 ;
-	uint32_t segments = 0 ;
-	uint32_t k = 0, depth_left = 0 ;
-	bool alive = false ;
-	Pcg rng ; rng.state = 0 ;
-	f3 ori = mk3( 0.f, 0.f, 0.f ), dir = mk3( 0.f, 0.f, 1.f ), thr = mk3( 1.f, 1.f, 1.f ) ;
+// The path tracer (see rtx_pool.cuh): one warp per CTA, persistent; a warp takes an 8x4 pixel
+// tile, traces all its paths -- 32*spp of them, RTX_K*32 in flight -- and writes the tile's
+// fixed-point sums.  Tiles are handed out through a global counter.
+#define RTX_POOL_R ( 32*RTX_K )
+__global__ void __launch_bounds__( 32 ) k_render( const FrameArgs a, uint32_t* tile_counter, int32_t* ovf_all ) {
+	__shared__ uint32_t words[F_WORDS*RTX_POOL_R] ;
+	__shared__ unsigned long long acc[32*3] ;
+	__shared__ uint32_t segs[32] ;
+	const uint32_t lane = threadIdx.x ;
+	const uint32_t lt = ( 1u<<lane )-1u ;
+	DevPool p ;
+	p.w = words ;
+	p.ovf = ovf_all+size_t( blockIdx.x )*RTX_POOL_R*RTX_POOL_OVF ;
+	const uint32_t tiles_x = ( a.w+7u )>>3, tiles_y = ( a.h+3u )>>2, n_tiles = tiles_x*tiles_y ;
 
 	while ( true ) {
-		if ( ! alive ) {
-			if ( k>=a.spp )
-				break ;
-			rng.seed( a.seed, pix, a.sample0+k*a.sample_stride ) ;
-			primary_ray( a.cam, x, y, a.w, a.h, rng, ori, dir ) ;
-			thr = mk3( 1.f, 1.f, 1.f ) ;
-			depth_left = a.depth ;
-			alive = true ;
-			k++ ;
-		}
-		HitRec hit ;
-		closest( a.S, ori, dir, 1e-3f, st, hit ) ;
-		segments++ ;
-		f3 c = mk3( 0.f, 0.f, 0.f ) ;
-		bool done = true ;
-		if ( hit.thing<0 )
-			c = thr*sky( dir ) ;
-		else if ( depth_left>0 ) {
-			Frame fr ;
-			frame_of( a.S, hit, ori, dir, 1e-3f, fr ) ;
-			f3 att, out ;
-			if ( scatter( a.S.shade+hit.thing, dir, fr, rng, att, out ) ) {
-				thr = thr*att ;
-				ori = fr.p ; dir = out ; depth_left-- ;
-				done = false ;
-			}
-		}
-		if ( done ) {
-			acc0 += tofix( c.x ) ; acc1 += tofix( c.y ) ; acc2 += tofix( c.z ) ;
-			alive = false ;
-		}
-	}
+		uint32_t tile = 0 ;
+		if ( lane == 0 ) tile = atomicAdd( tile_counter, 1u ) ;
+		tile = __shfl_sync( 0xffffffffu, tile, 0 ) ;
+		if ( tile>=n_tiles )
+			break ;
+		const uint32_t x0 = ( tile%tiles_x )*8u, y0 = ( tile/tiles_x )*4u ;
+		acc[lane] = 0 ; acc[lane+32] = 0 ; acc[lane+64] = 0 ; segs[lane] = 0 ;
+		const uint32_t vmask = __ballot_sync( 0xffffffffu, x0+( lane&7u )<a.w && y0+( lane>>3 )<a.h ) ;
+		const uint32_t n_valid = __popc( vmask ) ;
+		const uint32_t total = n_valid*a.spp ;   // paths of this tile: index = sample*n_valid + (rank of pixel)
+		uint32_t next = 0 ;
+		int kinds[RTX_K] ;
+#pragma unroll
+		for ( int j = 0 ; j<RTX_K ; j++ ) kinds[j] = K_REGEN ;
+		__syncwarp() ;
 
-	ulonglong2* out = reinterpret_cast<ulonglong2*>( a.accum+4*size_t( pix ) ) ;
-	ulonglong2 lo = make_ulonglong2( acc0, acc1 ), hi = make_ulonglong2( acc2, uint64_t( segments ) ) ;
-	if ( a.accumulate ) {
-		const ulonglong2 plo = out[0], phi = out[1] ;
-		lo.x += plo.x ; lo.y += plo.y ; hi.x += phi.x ; hi.y += phi.y ;
+		while ( true ) {
+			// vote: which step kind can most lanes take?
+			uint32_t mine = 0 ;
+#pragma unroll
+			for ( int j = 0 ; j<RTX_K ; j++ ) mine |= 1u<<kinds[j] ;
+			int kind = K_DONE ; int most = 0 ;
+#pragma unroll
+			for ( int k = 1 ; k<K_KINDS ; k++ ) {
+				const int n = __popc( __ballot_sync( 0xffffffffu, ( mine>>k )&1u ) ) ;
+				if ( n>most ) { most = n ; kind = k ; }
+			}
+			if ( kind == K_DONE )
+				break ;
+			int j = -1 ;
+#pragma unroll
+			for ( int jj = RTX_K-1 ; jj>=0 ; jj-- ) if ( kinds[jj] == kind ) j = jj ;
+			const int slot = j*32+int( lane ) ;
+			int nk = kind ;
+			switch ( kind ) {
+				case K_NODE:
+					if ( j>=0 ) nk = step_node( p, slot, a.S ) ;
+					break ;
+				case K_LEAF:
+					if ( j>=0 ) nk = step_leaf( p, slot, a.S ) ;
+					break ;
+				case K_THING:
+					if ( j>=0 ) nk = step_thing( p, slot, a.S ) ;
+					break ;
+				case K_SHADE:
+					if ( j>=0 ) {
+						f3 c ;
+						nk = step_shade( p, slot, a.S, c ) ;
+						const uint32_t px = uint32_t( p.i( F_PIX, slot ) ) ;
+						atomicAdd( segs+px, 1u ) ;
+						if ( nk == K_REGEN ) {
+							atomicAdd( acc+px, ( unsigned long long ) tofix( c.x ) ) ;
+							atomicAdd( acc+32+px, ( unsigned long long ) tofix( c.y ) ) ;
+							atomicAdd( acc+64+px, ( unsigned long long ) tofix( c.z ) ) ;
+						}
+					}
+					break ;
+				default: {   // K_REGEN
+					const uint32_t want = __ballot_sync( 0xffffffffu, j>=0 ) ;
+					const uint32_t idx = next+__popc( want&lt ) ;
+					next += __popc( want ) ;
+					if ( j>=0 ) {
+						if ( idx<total ) {
+							const uint32_t px = __fns( vmask, 0, int( idx%n_valid )+1 ) ;   // idx%n_valid-th valid pixel of the tile
+							nk = step_regen( p, slot, a.S, a.cam, x0+( px&7u ), y0+( px>>3 ), a.w, a.h, px, a.seed, a.sample0+( idx/n_valid )*a.sample_stride, a.depth ) ;
+						} else
+							nk = K_DONE ;
+					}
+				}
+			}
+#pragma unroll
+			for ( int jj = 0 ; jj<RTX_K ; jj++ ) if ( jj == j ) kinds[jj] = nk ;
+		}
+		__syncwarp() ;
+
+		if ( ( vmask>>lane )&1u ) {
+			const uint32_t pix = a.w*( y0+( lane>>3 ) )+x0+( lane&7u ) ;
+			ulonglong2* out = reinterpret_cast<ulonglong2*>( a.accum+4*size_t( pix ) ) ;
+			ulonglong2 lo = make_ulonglong2( acc[lane], acc[32+lane] ), hi = make_ulonglong2( acc[64+lane], ( unsigned long long ) segs[lane] ) ;
+			if ( a.accumulate ) {
+				const ulonglong2 plo = out[0], phi = out[1] ;
+				lo.x += plo.x ; lo.y += plo.y ; hi.x += phi.x ; hi.y += phi.y ;
+			}
+			out[0] = lo ; out[1] = hi ;
+		}
+		__syncwarp() ;
 	}
-	out[0] = lo ; out[1] = hi ;
 }
 
 // first hit of the primary ray of sample `sample0` of every pixel
 __global__ void __launch_bounds__( RTX_BLOCK ) k_primary_hits( const FrameArgs a ) {
 	__shared__ int32_t stack_mem[RTX_SM_STACK*RTX_BLOCK] ;
 	uint32_t x, y ;
-	if ( ! tile_pixel( a.w, a.h, x, y ) )
-		return ;
+	const bool valid = tile_pixel( a.w, a.h, x, y ) ;
 	const uint32_t pix = a.w*y+x ;
 	DevStack st ;
 	st.base = stack_mem+threadIdx.x ;
@@ -139,41 +182,44 @@ __global__ void __launch_bounds__( RTX_BLOCK ) k_primary_hits( const FrameArgs a
 	f3 ori, dir ;
 	primary_ray( a.cam, x, y, a.w, a.h, rng, ori, dir ) ;
 	HitRec hit ;
-	closest( a.S, ori, dir, 1e-3f, st, hit ) ;
+	closest( a.S, ori, dir, 1e-3f, st, hit, valid ) ;
+	if ( ! valid )
+		return ;
 	a.hit_id[pix] = hit.thing<0 ? int64_t( -1 ) : ( ( int64_t( hit.thing )<<32 )|int64_t( uint32_t( hit.prim+1 ) ) ) ;
 	a.hit_t[pix]  = hit.thing<0 ? -1.f : hit.t ;
 }
 
 // picker (optx/camera_i.cu:27-29, optx/optics_i.cu:25-29): one primary ray through
-// (px,py), the thing id or UINT_MAX
+// (px,py), the thing id or UINT_MAX.  Launched as one warp; lane 0 carries the ray.
 __global__ void k_pick( const FrameArgs a, uint32_t px, uint32_t py, uint32_t* pick_id ) {
 	__shared__ int32_t stack_mem[RTX_SM_STACK*RTX_BLOCK] ;
-	if ( threadIdx.x != 0 || blockIdx.x != 0 )
-		return ;
 	DevStack st ;
-	st.base = stack_mem ;
+	st.base = stack_mem+threadIdx.x ;
 	Pcg rng ;
 	rng.seed( a.seed, a.w*py+px, a.sample0 ) ;
 	f3 ori, dir ;
 	primary_ray( a.cam, px, py, a.w, a.h, rng, ori, dir ) ;
 	HitRec hit ;
-	closest( a.S, ori, dir, 1e-3f, st, hit ) ;
-	*pick_id = hit.thing<0 ? 0xffffffffu : uint32_t( hit.thing ) ;
+	closest( a.S, ori, dir, 1e-3f, st, hit, threadIdx.x == 0 ) ;
+	if ( threadIdx.x == 0 )
+		*pick_id = hit.thing<0 ? 0xffffffffu : uint32_t( hit.thing ) ;
 }
 
 // closest hits of caller-supplied rays: through the LBVH, or by exhaustive scan
 __global__ void __launch_bounds__( RTX_BLOCK ) k_trace_rays( const SceneDev S, uint32_t n, const float* ori, const float* dir, float tmin, int brute, int64_t* id, float* t ) {
 	__shared__ int32_t stack_mem[RTX_SM_STACK*RTX_BLOCK] ;
 	const uint32_t r = blockIdx.x*RTX_BLOCK+threadIdx.x ;
-	if ( r>=n )
-		return ;
+	const bool valid = r<n ;
+	const uint32_t q = valid ? r : 0u ;
 	DevStack st ;
 	st.base = stack_mem+threadIdx.x ;
-	const f3 o = mk3( ori[3*size_t( r )], ori[3*size_t( r )+1], ori[3*size_t( r )+2] ) ;
-	const f3 d = mk3( dir[3*size_t( r )], dir[3*size_t( r )+1], dir[3*size_t( r )+2] ) ;
+	const f3 o = mk3( ori[3*size_t( q )], ori[3*size_t( q )+1], ori[3*size_t( q )+2] ) ;
+	const f3 d = mk3( dir[3*size_t( q )], dir[3*size_t( q )+1], dir[3*size_t( q )+2] ) ;
 	HitRec hit ;
-	if ( brute ) closest_brute( S, o, d, tmin, hit ) ;
-	else         closest( S, o, d, tmin, st, hit ) ;
+	if ( brute ) { if ( valid ) closest_brute( S, o, d, tmin, hit ) ; }
+	else         closest( S, o, d, tmin, st, hit, valid ) ;
+	if ( ! valid )
+		return ;
 	id[r] = hit.thing<0 ? int64_t( -1 ) : ( ( int64_t( hit.thing )<<32 )|int64_t( uint32_t( hit.prim+1 ) ) ) ;
 	t[r]  = hit.thing<0 ? -1.f : hit.t ;
 }

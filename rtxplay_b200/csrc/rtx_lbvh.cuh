@@ -8,7 +8,8 @@
 //   k_karras          Karras 2012 radix-tree hierarchy over the sorted keys (ties broken
 //                     by position)
 //   k_refit           bottom-up AABB refit with per-node arrival counters
-//   k_emit            64-byte traversal nodes (both child boxes inline)
+//   k_wide_level      collapse of the binary tree into 4-wide, 128-byte traversal nodes with
+//                     multi-primitive leaves, one launch per level of the wide tree
 // Builder inputs are primitive AABBs, so the same code builds the per-mesh trees (over
 // triangles) and the top level (over thing bounds); refit alone serves Scene::update.
 #pragma once
@@ -52,7 +53,7 @@ RTX_HD int delta( const uint64_t* keys, int n, int i, int j ) {
 	return clz64( a^b ) ;
 }
 // inner node i of the radix tree: children and covered range
-RTX_HD void karras_node( const uint64_t* keys, int n, int i, int& left, int& right, bool& left_leaf, bool& right_leaf ) {
+RTX_HD void karras_node( const uint64_t* keys, int n, int i, int& left, int& right, bool& left_leaf, bool& right_leaf, int& range_lo, int& range_hi ) {
 	const int d = ( delta( keys, n, i, i+1 )-delta( keys, n, i, i-1 ) )>=0 ? 1 : -1 ;
 	const int dmin = delta( keys, n, i, i-d ) ;
 	int lmax = 2 ;
@@ -72,12 +73,52 @@ RTX_HD void karras_node( const uint64_t* keys, int n, int i, int& left, int& rig
 	const int lo = i<j ? i : j, hi = i<j ? j : i ;
 	left = gamma ; right = gamma+1 ;
 	left_leaf = ( lo == gamma ) ; right_leaf = ( hi == gamma+1 ) ;
+	range_lo = lo ; range_hi = hi ;
 }
 // pad a box so that rounding in the (float) slab test can never exclude a primitive hit
 RTX_HD void pad_box( f3& lo, f3& hi ) {
 	const float m = fmaxf( fmaxf( fmaxf( fabsf( lo.x ), fabsf( hi.x ) ), fmaxf( fabsf( lo.y ), fabsf( hi.y ) ) ), fmaxf( fabsf( lo.z ), fabsf( hi.z ) ) ) ;
 	const float e = m*( 1.f/8192.f )+1e-30f ;
 	lo = mk3( lo.x-e, lo.y-e, lo.z-e ) ; hi = mk3( hi.x+e, hi.y+e, hi.z+e ) ;
+}
+
+// Collapse step: the up to RTX_WIDTH children of the wide node that replaces binary inner
+// node `bin`.  Starts from its two children and keeps opening the slot with the largest
+// box area, as long as that slot is an inner node covering more than leaf_max primitives.
+// Slots: >= 0 binary inner node, < 0 binary leaf slot ~s.  Binary boxes: [0,n-1) inner,
+// [n-1,2n-1) leaves.  (Inner node i covers the sorted range child-range[i].)
+RTX_HD float box_area( const q4& lo, const q4& hi ) {
+	const float dx = hi.x-lo.x, dy = hi.y-lo.y, dz = hi.z-lo.z ;
+	return dx*dy+dy*dz+dz*dx ;
+}
+template <class I2>
+RTX_HD int wide_gather( int bin, const I2* child, const I2* range, const q4* blo, const q4* bhi, int n, int leaf_max, int slots[RTX_WIDTH] ) {
+	int ns = 2 ;
+	slots[0] = child[bin].x ; slots[1] = child[bin].y ;
+	while ( ns<RTX_WIDTH ) {
+		int pick = -1 ; float amax = -1.f ;
+		for ( int k = 0 ; k<ns ; k++ ) {
+			const int s = slots[k] ;
+			if ( s<0 || range[s].y-range[s].x+1<=leaf_max )
+				continue ;
+			const float a = box_area( blo[s], bhi[s] ) ;
+			if ( a>amax ) { amax = a ; pick = k ; }
+		}
+		if ( pick<0 )
+			break ;
+		const int s = slots[pick] ;
+		slots[pick] = child[s].x ;
+		slots[ns++] = child[s].y ;
+	}
+	return ns ;
+}
+// leaf ref of a slot that ends the wide tree: a binary leaf, or an inner node small enough
+template <class I2>
+RTX_HD bool wide_leaf_ref( int s, const I2* range, int leaf_max, int& ref ) {
+	if ( s<0 ) { ref = ~( ( ( ~s )<<3 )|0 ) ; return true ; }
+	const int cnt = range[s].y-range[s].x+1 ;
+	if ( cnt<=leaf_max ) { ref = ~( ( range[s].x<<3 )|( cnt-1 ) ) ; return true ; }
+	return false ;
 }
 
 #if defined( __CUDACC__ )
@@ -178,12 +219,13 @@ __global__ void __launch_bounds__( 32 ) k_radix_scatter( const uint64_t* keys, c
 
 // ---- hierarchy -----------------------------------------------------------------------
 // child encoding inside the builder: >=0 inner node, <0 leaf slot ~c
-__global__ void __launch_bounds__( 256 ) k_karras( const uint64_t* keys, int n, int2* child, int* parent_inner, int* parent_leaf ) {
+__global__ void __launch_bounds__( 256 ) k_karras( const uint64_t* keys, int n, int2* child, int2* range, int* parent_inner, int* parent_leaf ) {
 	const int i = blockIdx.x*blockDim.x+threadIdx.x ;
 	if ( i>=n-1 ) return ;
-	int l, r ; bool ll, rl ;
-	karras_node( keys, n, i, l, r, ll, rl ) ;
+	int l, r, lo, hi ; bool ll, rl ;
+	karras_node( keys, n, i, l, r, ll, rl, lo, hi ) ;
 	child[i] = make_int2( ll ? ~l : l, rl ? ~r : r ) ;
+	range[i] = make_int2( lo, hi ) ;
 	if ( ll ) parent_leaf[l] = i ; else parent_inner[l] = i ;
 	if ( rl ) parent_leaf[r] = i ; else parent_inner[r] = i ;
 	if ( i == 0 ) parent_inner[0] = -1 ;
@@ -217,27 +259,39 @@ __global__ void __launch_bounds__( 256 ) k_refit( const q4* plo, const q4* phi, 
 	}
 }
 
-// traversal nodes: leaf refs become ~(slot<<2 | 0) (one primitive per leaf)
-__global__ void __launch_bounds__( 256 ) k_emit( int n, const int2* child, const q4* blo, const q4* bhi, q4* nodes ) {
-	const int i = blockIdx.x*blockDim.x+threadIdx.x ;
+// One level of the wide tree: work item = (binary inner node, wide node index).  Children
+// that stay inner get a fresh wide index and become work items of the next level.
+// counters[0] = wide nodes allocated so far, counters[1] = size of the next frontier.
+__global__ void __launch_bounds__( 128 ) k_wide_level( const int2* frontier, uint32_t n_front, int n, int leaf_max, const int2* child, const int2* range, const q4* blo, const q4* bhi, q4* nodes, int2* next, uint32_t* counters ) {
+	const uint32_t w = blockIdx.x*blockDim.x+threadIdx.x ;
+	if ( w>=n_front ) return ;
+	const int2 item = frontier[w] ;
+	float lo[3][RTX_WIDTH], hi[3][RTX_WIDTH] ; int ref[RTX_WIDTH] ;
+	for ( int k = 0 ; k<RTX_WIDTH ; k++ ) { ref[k] = RTX_REF_EMPTY ; for ( int a = 0 ; a<3 ; a++ ) { lo[a][k] = 0.f ; hi[a][k] = 0.f ; } }
 	if ( n == 1 ) {
-		if ( i == 0 ) {
-			const int ref = ~0 ;   // slot 0, count 1
-			nodes[0] = { blo[0].x, blo[0].y, blo[0].z, __int_as_float( ref ) } ;
-			nodes[1] = { bhi[0].x, bhi[0].y, bhi[0].z, __int_as_float( ref ) } ;
-			nodes[2] = nodes[0] ; nodes[3] = nodes[1] ;
+		ref[0] = ~0 ;   // the single primitive: slot 0, count 1
+		lo[0][0] = blo[0].x ; lo[1][0] = blo[0].y ; lo[2][0] = blo[0].z ; hi[0][0] = bhi[0].x ; hi[1][0] = bhi[0].y ; hi[2][0] = bhi[0].z ;
+	} else {
+		int slots[RTX_WIDTH] ;
+		const int ns = wide_gather( item.x, child, range, blo, bhi, n, leaf_max, slots ) ;
+		for ( int k = 0 ; k<ns ; k++ ) {
+			const int s = slots[k] ;
+			const int b = s<0 ? n-1+( ~s ) : s ;
+			lo[0][k] = blo[b].x ; lo[1][k] = blo[b].y ; lo[2][k] = blo[b].z ; hi[0][k] = bhi[b].x ; hi[1][k] = bhi[b].y ; hi[2][k] = bhi[b].z ;
+			if ( ! wide_leaf_ref( s, range, leaf_max, ref[k] ) ) {
+				const uint32_t idx = atomicAdd( counters, 1u ) ;
+				next[atomicAdd( counters+1, 1u )] = make_int2( s, int( idx ) ) ;
+				ref[k] = int( idx ) ;
+			}
 		}
-		return ;
 	}
-	if ( i>=n-1 ) return ;
-	const int2 c = child[i] ;
-	const int a = c.x<0 ? n-1+( ~c.x ) : c.x, b = c.y<0 ? n-1+( ~c.y ) : c.y ;
-	const int ra = c.x<0 ? ~( ( ~c.x )<<2 ) : c.x, rb = c.y<0 ? ~( ( ~c.y )<<2 ) : c.y ;
-	q4* o = nodes+size_t( i )*RTX_NODE_RECS ;
-	o[0] = { blo[a].x, blo[a].y, blo[a].z, __int_as_float( ra ) } ;
-	o[1] = { bhi[a].x, bhi[a].y, bhi[a].z, __int_as_float( rb ) } ;
-	o[2] = { blo[b].x, blo[b].y, blo[b].z, 0.f } ;
-	o[3] = { bhi[b].x, bhi[b].y, bhi[b].z, 0.f } ;
+	q4* o = nodes+size_t( item.y )*RTX_NODE_RECS ;
+	for ( int a = 0 ; a<3 ; a++ ) {
+		o[a]   = { lo[a][0], lo[a][1], lo[a][2], lo[a][3] } ;
+		o[3+a] = { hi[a][0], hi[a][1], hi[a][2], hi[a][3] } ;
+	}
+	o[6] = { __int_as_float( ref[0] ), __int_as_float( ref[1] ), __int_as_float( ref[2] ), __int_as_float( ref[3] ) } ;
+	o[7] = { 0.f, 0.f, 0.f, 0.f } ;
 }
 
 // ---- primitive boxes -------------------------------------------------------------------

@@ -1,0 +1,284 @@
+// rtx_pool.cuh -- the path tracer as a warp-scheduled state machine.
+//
+// Why: traced rays need very different work -- inner nodes, triangle leaves, instance
+// entries, shading, new paths -- and a warp that binds one ray to one lane spends most of
+// its issue slots on a handful of lanes (measured on B200, ncu: 6.9 of 32 lanes active,
+// profiles/r01_v0_*).  Here every lane owns RTX_K ray slots whose state lives in shared
+// memory (SoA over slots: word f of slot s at [f*R+s], s = j*32+lane, so a lane only ever
+// touches bank `lane` -- conflict-free by construction).  Each iteration the warp votes
+// (ballot) for the step kind most lanes can take, and every lane advances ONE of its rays
+// of that kind by one step:
+//     NODE   test the four children of a wide BVH node, push / pop
+//     LEAF   test the 1..4 triangles of a mesh leaf
+//     THING  top-level leaf: analytic sphere test, or transform the ray into a mesh
+//     SHADE  ray finished: sky or scatter, start the next ray of the path
+//     REGEN  path finished: fetch the next (pixel, sample) of the warp's tile
+// Rays of other kinds wait in their slots; while a ray waits, the node it needs next has
+// already been prefetched.  Results do not depend on the schedule: closest hits are
+// order-independent (rtx_core.cuh better()), every path owns its random stream, and
+// radiance is summed in fixed point.
+//
+// The step functions are templated on the slot store so that the host harness can run the
+// very same code serially (tests/hostemu).
+#pragma once
+
+#include "rtx_core.cuh"
+
+namespace rtx {
+
+#ifndef RTX_K
+#define RTX_K 3                 // ray slots per lane
+#endif
+#define RTX_POOL_STACK 16       // stack entries per slot kept in shared memory
+#define RTX_POOL_OVF   80       // further entries per slot in a global overflow area
+
+// slot fields (32-bit words)
+enum {
+	F_OX, F_OY, F_OZ, F_DX, F_DY, F_DZ,                      // world ray
+	F_HX, F_HY, F_HZ, F_LX, F_LY, F_LZ, F_EX, F_EY, F_EZ,    // object ray: origin hi, lo; direction
+	F_IX, F_IY, F_IZ, F_QX, F_QY, F_QZ,                      // current level: 1/d, o/d
+	F_T, F_THING, F_PRIM, F_U, F_V,                          // best hit so far
+	F_CUR, F_LEVEL, F_SP,                                    // next work item; thing being traversed (-1: top); stack size
+	F_NODES0, F_NODES1, F_TRIS0, F_TRIS1,                    // node / triangle arrays of the current level
+	F_THRX, F_THRY, F_THRZ, F_RNG0, F_RNG1, F_PIX, F_META,   // path: throughput, stream, tile pixel, sample<<8|depth left
+	F_STACK,
+	F_WORDS = F_STACK+RTX_POOL_STACK
+} ;
+
+enum { K_DONE = 0, K_NODE = 1, K_LEAF = 2, K_THING = 3, K_SHADE = 4, K_REGEN = 5, K_KINDS = 6 } ;
+
+// ---- slot store on the device: shared memory, SoA, plus the global overflow stack
+#if defined( __CUDACC__ )
+struct DevPool {
+	uint32_t* w ;      // this warp's words, [F_WORDS][R]
+	int32_t*  ovf ;    // this warp's overflow area, [R][RTX_POOL_OVF]
+	__device__ __forceinline__ float    f( int fld, int slot ) const { return __uint_as_float( w[fld*( 32*RTX_K )+slot] ) ; }
+	__device__ __forceinline__ int32_t  i( int fld, int slot ) const { return int32_t( w[fld*( 32*RTX_K )+slot] ) ; }
+	__device__ __forceinline__ void     sf( int fld, int slot, float v ) { w[fld*( 32*RTX_K )+slot] = __float_as_uint( v ) ; }
+	__device__ __forceinline__ void     si( int fld, int slot, int32_t v ) { w[fld*( 32*RTX_K )+slot] = uint32_t( v ) ; }
+	__device__ __forceinline__ void     push( int slot, int32_t& sp, int32_t v ) {
+		if ( sp<RTX_POOL_STACK ) w[( F_STACK+sp )*( 32*RTX_K )+slot] = uint32_t( v ) ;
+		else if ( sp<RTX_POOL_STACK+RTX_POOL_OVF ) ovf[slot*RTX_POOL_OVF+( sp-RTX_POOL_STACK )] = v ;
+		sp++ ;
+	}
+	__device__ __forceinline__ int32_t  pop( int slot, int32_t& sp ) {
+		sp-- ;
+		if ( sp<RTX_POOL_STACK ) return int32_t( w[( F_STACK+sp )*( 32*RTX_K )+slot] ) ;
+		return sp<RTX_POOL_STACK+RTX_POOL_OVF ? ovf[slot*RTX_POOL_OVF+( sp-RTX_POOL_STACK )] : RTX_STK_DONE ;
+	}
+} ;
+#endif
+
+template <class P> RTX_HD f3 ld3( const P& p, int fld, int slot ) { return mk3( p.f( fld, slot ), p.f( fld+1, slot ), p.f( fld+2, slot ) ) ; }
+template <class P> RTX_HD void st3( P& p, int fld, int slot, const f3& v ) { p.sf( fld, slot, v.x ) ; p.sf( fld+1, slot, v.y ) ; p.sf( fld+2, slot, v.z ) ; }
+template <class P, class T> RTX_HD const T* ldp( const P& p, int fld, int slot ) {
+	const uint64_t a = uint64_t( uint32_t( p.i( fld, slot ) ) )|( uint64_t( uint32_t( p.i( fld+1, slot ) ) )<<32 ) ;
+	return reinterpret_cast<const T*>( a ) ;
+}
+template <class P> RTX_HD void stp( P& p, int fld, int slot, const void* ptr ) {
+	const uint64_t a = reinterpret_cast<uint64_t>( ptr ) ;
+	p.si( fld, slot, int32_t( uint32_t( a ) ) ) ; p.si( fld+1, slot, int32_t( uint32_t( a>>32 ) ) ) ;
+}
+
+RTX_HD void prefetch_line( const void* a ) {
+#if defined( __CUDA_ARCH__ )
+	asm volatile( "prefetch.global.L1 [%0];" :: "l"( a ) ) ;
+#else
+	( void ) a ;
+#endif
+}
+
+// kind of the work item `cur` for a ray at the top level (level < 0) or inside a mesh
+RTX_HD int kind_of( int32_t cur, int32_t level ) {
+	if ( uint32_t( cur )<uint32_t( RTX_REF_EMPTY ) ) return K_NODE ;
+	if ( cur == RTX_STK_DONE ) return K_SHADE ;
+	return level<0 ? K_THING : K_LEAF ;
+}
+
+// world-space traversal state of a fresh ray
+template <class P> RTX_HD void begin_ray( P& p, int slot, const SceneDev& S, const f3& o, const f3& d ) {
+	st3( p, F_OX, slot, o ) ; st3( p, F_DX, slot, d ) ;
+	const f3 idir = mk3( safe_rcp( d.x ), safe_rcp( d.y ), safe_rcp( d.z ) ) ;
+	st3( p, F_IX, slot, idir ) ; st3( p, F_QX, slot, mk3( o.x*idir.x, o.y*idir.y, o.z*idir.z ) ) ;
+	p.sf( F_T, slot, INFINITY ) ; p.si( F_THING, slot, -1 ) ; p.si( F_PRIM, slot, -1 ) ;
+	p.si( F_LEVEL, slot, -1 ) ;
+	stp( p, F_NODES0, slot, S.tlas_nodes ) ; stp( p, F_TRIS0, slot, nullptr ) ;
+	int32_t sp = 0 ;
+	p.push( slot, sp, RTX_STK_DONE ) ;
+	p.si( F_SP, slot, sp ) ;
+	p.si( F_CUR, slot, S.n_things ? 0 : RTX_STK_DONE ) ;   // 0 = root of the top level
+	if ( S.n_things ) prefetch_line( S.tlas_nodes ) ;
+}
+
+// pop the next work item; leaving a mesh (RTX_STK_RETURN) is handled on the way
+template <class P> RTX_HD int32_t pop_next( P& p, int slot, const SceneDev& S, int32_t& sp, int32_t& level ) {
+	int32_t cur = p.pop( slot, sp ) ;
+	if ( cur == RTX_STK_RETURN ) {
+		const f3 o = ld3( p, F_OX, slot ), d = ld3( p, F_DX, slot ) ;
+		const f3 idir = mk3( safe_rcp( d.x ), safe_rcp( d.y ), safe_rcp( d.z ) ) ;
+		st3( p, F_IX, slot, idir ) ; st3( p, F_QX, slot, mk3( o.x*idir.x, o.y*idir.y, o.z*idir.z ) ) ;
+		level = -1 ;
+		p.si( F_LEVEL, slot, -1 ) ;
+		stp( p, F_NODES0, slot, S.tlas_nodes ) ; stp( p, F_TRIS0, slot, nullptr ) ;
+		cur = p.pop( slot, sp ) ;
+	}
+	return cur ;
+}
+
+// store the next work item and prefetch what it will read
+template <class P> RTX_HD int finish_step( P& p, int slot, int32_t cur, int32_t sp, int32_t level ) {
+	p.si( F_CUR, slot, cur ) ; p.si( F_SP, slot, sp ) ;
+	const int kind = kind_of( cur, level ) ;
+	if ( kind == K_NODE )
+		prefetch_line( ldp<P, q4>( p, F_NODES0, slot )+size_t( cur )*RTX_NODE_RECS ) ;
+	else if ( kind == K_LEAF )
+		prefetch_line( ldp<P, q4>( p, F_TRIS0, slot )+size_t( uint32_t( ~cur )>>3 )*3 ) ;
+	return kind ;
+}
+
+// ---- NODE: four slab tests, nearest child next, the other hits pushed far to near
+template <class P> RTX_HD int step_node( P& p, int slot, const SceneDev& S ) {
+	int32_t cur = p.i( F_CUR, slot ), sp = p.i( F_SP, slot ), level = p.i( F_LEVEL, slot ) ;
+	const f3 idir = ld3( p, F_IX, slot ), ood = ld3( p, F_QX, slot ) ;
+	const float tbest_s = p.f( F_T, slot )*RTX_SLACK ;
+	const float tmin = 1e-3f ;
+	const q4* n = ldp<P, q4>( p, F_NODES0, slot )+size_t( cur )*RTX_NODE_RECS ;
+	const q4 lx = ldq( n ), ly = ldq( n+1 ), lz = ldq( n+2 ), hx = ldq( n+3 ), hy = ldq( n+4 ), hz = ldq( n+5 ), rf = ldq( n+6 ) ;
+	int32_t c0 = asint( rf.x ), c1 = asint( rf.y ), c2 = asint( rf.z ), c3 = asint( rf.w ) ;
+	float t0 = slab( lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, idir, ood, tmin, tbest_s ) ;
+	float t1 = slab( lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, idir, ood, tmin, tbest_s ) ;
+	float t2 = slab( lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, idir, ood, tmin, tbest_s ) ;
+	float t3 = slab( lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, idir, ood, tmin, tbest_s ) ;
+	if ( c0 == RTX_REF_EMPTY ) t0 = INFINITY ;
+	if ( c1 == RTX_REF_EMPTY ) t1 = INFINITY ;
+	if ( c2 == RTX_REF_EMPTY ) t2 = INFINITY ;
+	if ( c3 == RTX_REF_EMPTY ) t3 = INFINITY ;
+#define RTX_CSWAP( ta, ca, tb, cb ) if ( tb<ta ) { const float tt = ta ; ta = tb ; tb = tt ; const int32_t cc = ca ; ca = cb ; cb = cc ; }
+	RTX_CSWAP( t0, c0, t1, c1 ) RTX_CSWAP( t2, c2, t3, c3 ) RTX_CSWAP( t0, c0, t2, c2 ) RTX_CSWAP( t1, c1, t3, c3 ) RTX_CSWAP( t1, c1, t2, c2 )
+#undef RTX_CSWAP
+	if ( t0 == INFINITY )
+		cur = pop_next( p, slot, S, sp, level ) ;
+	else {
+		if ( t3<INFINITY ) p.push( slot, sp, c3 ) ;
+		if ( t2<INFINITY ) p.push( slot, sp, c2 ) ;
+		if ( t1<INFINITY ) p.push( slot, sp, c1 ) ;
+		cur = c0 ;
+	}
+	return finish_step( p, slot, cur, sp, level ) ;
+}
+
+// ---- LEAF: the triangles of a mesh leaf
+template <class P> RTX_HD int step_leaf( P& p, int slot, const SceneDev& S ) {
+	int32_t cur = p.i( F_CUR, slot ), sp = p.i( F_SP, slot ), level = p.i( F_LEVEL, slot ) ;
+	const uint32_t ref = uint32_t( ~cur ) ;
+	const uint32_t first = ref>>3, count = ( ref&7u )+1u ;
+	const f3 ohi = ld3( p, F_HX, slot ), olo = ld3( p, F_LX, slot ), dd = ld3( p, F_EX, slot ) ;
+	HitRec best ;
+	best.t = p.f( F_T, slot ) ; best.thing = p.i( F_THING, slot ) ; best.prim = p.i( F_PRIM, slot ) ; best.u = 0.f ; best.v = 0.f ;
+	const q4* tris = ldp<P, q4>( p, F_TRIS0, slot ) ;
+	bool changed = false ;
+	for ( uint32_t k = 0 ; k<count ; k++ ) {
+		const q4* T = tris+size_t( first+k )*3 ;
+		const q4 a = ldq( T ), b = ldq( T+1 ), c = ldq( T+2 ) ;
+		float t, u, v ;
+		if ( tri_test( mk3( a.x, a.y, a.z ), mk3( b.x, b.y, b.z ), mk3( c.x, c.y, c.z ), ohi, olo, dd, 1e-3f, t, u, v ) ) {
+			const int32_t prim = asint( a.w ) ;
+			if ( better( t, level, prim, best ) ) {
+				best.t = t ; best.thing = level ; best.prim = prim ; best.u = u ; best.v = v ;
+				changed = true ;
+			}
+		}
+	}
+	if ( changed ) {
+		p.sf( F_T, slot, best.t ) ; p.si( F_THING, slot, best.thing ) ; p.si( F_PRIM, slot, best.prim ) ;
+		p.sf( F_U, slot, best.u ) ; p.sf( F_V, slot, best.v ) ;
+	}
+	cur = pop_next( p, slot, S, sp, level ) ;
+	return finish_step( p, slot, cur, sp, level ) ;
+}
+
+// ---- THING: a top-level leaf (one thing): analytic sphere, or enter its mesh
+template <class P> RTX_HD int step_thing( P& p, int slot, const SceneDev& S ) {
+	int32_t cur = p.i( F_CUR, slot ), sp = p.i( F_SP, slot ), level = -1 ;
+	const uint32_t first = uint32_t( ~cur )>>3 ;
+	const int32_t k = int32_t( RTX_LDG( S.tlas_order+first ) ) ;
+	const ThingTrav* tt = S.trav+k ;
+	const f3 o = ld3( p, F_OX, slot ), d = ld3( p, F_DX, slot ) ;
+	const double m0 = RTX_LDG( tt->inv+0 ), m1 = RTX_LDG( tt->inv+1 ), m2 = RTX_LDG( tt->inv+2 ), m3 = RTX_LDG( tt->inv+3 ) ;
+	if ( RTX_LDG( &tt->kind ) == 0 ) {
+		double td ;
+		if ( sphere_root( mk3( m0, m1, m2 ), m3, wide( o ), wide( d ), double( 1e-3f ), td ) ) {
+			const float t = float( td ) ;
+			HitRec best ;
+			best.t = p.f( F_T, slot ) ; best.thing = p.i( F_THING, slot ) ; best.prim = p.i( F_PRIM, slot ) ;
+			if ( better( t, k, -1, best ) ) {
+				p.sf( F_T, slot, t ) ; p.si( F_THING, slot, k ) ; p.si( F_PRIM, slot, -1 ) ;
+			}
+		}
+		cur = pop_next( p, slot, S, sp, level ) ;
+		return finish_step( p, slot, cur, sp, level ) ;
+	}
+	// enter the mesh: object-space ray, origin in double carried as hi+lo
+	double m[12] ;
+	m[0] = m0 ; m[1] = m1 ; m[2] = m2 ; m[3] = m3 ;
+	for ( int j = 4 ; j<12 ; j++ ) m[j] = RTX_LDG( tt->inv+j ) ;
+	const d3 od = xfpoint( m, wide( o ) ) ;
+	const f3 ohi = narrow( od ) ;
+	const f3 olo = narrow( od-wide( ohi ) ) ;
+	const f3 dd  = narrow( xfvec( m, wide( d ) ) ) ;
+	const f3 idir = mk3( safe_rcp( dd.x ), safe_rcp( dd.y ), safe_rcp( dd.z ) ) ;
+	st3( p, F_HX, slot, ohi ) ; st3( p, F_LX, slot, olo ) ; st3( p, F_EX, slot, dd ) ;
+	st3( p, F_IX, slot, idir ) ; st3( p, F_QX, slot, mk3( ohi.x*idir.x, ohi.y*idir.y, ohi.z*idir.z ) ) ;
+	stp( p, F_NODES0, slot, ldptr( &tt->nodes ) ) ; stp( p, F_TRIS0, slot, ldptr( &tt->tris ) ) ;
+	p.si( F_LEVEL, slot, k ) ;
+	p.push( slot, sp, RTX_STK_RETURN ) ;
+	return finish_step( p, slot, 0, sp, k ) ;
+}
+
+// ---- SHADE: the ray is finished.  Returns K_NODE/K_SHADE (path continues with a new ray)
+// or K_REGEN (path ended; `c` is its colour).  rtow.cxx:34-49.
+template <class P> RTX_HD int step_shade( P& p, int slot, const SceneDev& S, f3& c ) {
+	HitRec h ;
+	h.t = p.f( F_T, slot ) ; h.thing = p.i( F_THING, slot ) ; h.prim = p.i( F_PRIM, slot ) ; h.u = p.f( F_U, slot ) ; h.v = p.f( F_V, slot ) ;
+	const f3 ori = ld3( p, F_OX, slot ), dir = ld3( p, F_DX, slot ) ;
+	f3 thr = ld3( p, F_THRX, slot ) ;
+	const uint32_t meta = uint32_t( p.i( F_META, slot ) ) ;
+	const uint32_t depth_left = meta&255u ;
+	c = mk3( 0.f, 0.f, 0.f ) ;
+	if ( h.thing<0 ) {
+		c = thr*sky( dir ) ;
+		return K_REGEN ;
+	}
+	if ( depth_left == 0 )
+		return K_REGEN ;
+	Frame fr ;
+	frame_of( S, h, ori, dir, 1e-3f, fr ) ;
+	Pcg rng ;
+	rng.state = uint64_t( uint32_t( p.i( F_RNG0, slot ) ) )|( uint64_t( uint32_t( p.i( F_RNG1, slot ) ) )<<32 ) ;
+	f3 att, out ;
+	if ( ! scatter( S.shade+h.thing, dir, fr, rng, att, out ) )
+		return K_REGEN ;
+	thr = thr*att ;
+	st3( p, F_THRX, slot, thr ) ;
+	p.si( F_RNG0, slot, int32_t( uint32_t( rng.state ) ) ) ; p.si( F_RNG1, slot, int32_t( uint32_t( rng.state>>32 ) ) ) ;
+	p.si( F_META, slot, int32_t( meta-1u ) ) ;
+	begin_ray( p, slot, S, fr.p, out ) ;
+	return kind_of( p.i( F_CUR, slot ), -1 ) ;
+}
+
+// ---- REGEN: a new path (pixel x,y of the image, tile-local pixel slot, global sample index)
+template <class P> RTX_HD int step_regen( P& p, int slot, const SceneDev& S, const CameraDev& cam, uint32_t x, uint32_t y, uint32_t w, uint32_t h,
+		uint32_t tile_pixel, uint64_t seed, uint32_t sample, uint32_t depth ) {
+	Pcg rng ;
+	rng.seed( seed, w*y+x, sample ) ;
+	f3 ori, dir ;
+	primary_ray( cam, x, y, w, h, rng, ori, dir ) ;
+	st3( p, F_THRX, slot, mk3( 1.f, 1.f, 1.f ) ) ;
+	p.si( F_RNG0, slot, int32_t( uint32_t( rng.state ) ) ) ; p.si( F_RNG1, slot, int32_t( uint32_t( rng.state>>32 ) ) ) ;
+	p.si( F_PIX, slot, int32_t( tile_pixel ) ) ;
+	p.si( F_META, slot, int32_t( depth>255u ? 255u : depth ) ) ;
+	begin_ray( p, slot, S, ori, dir ) ;
+	return kind_of( p.i( F_CUR, slot ), -1 ) ;
+}
+
+} // namespace rtx

@@ -22,7 +22,7 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 
 
-def render(things, cam, w, h, spp, depth=50, seed=4711, sample0=0, sample_stride=1, meshes=None, brute=False):
+def render(things, cam, w, h, spp, depth=50, seed=4711, sample0=0, sample_stride=1, meshes=None, brute=False, pool=True):
     L = lib()
     things = np.ascontiguousarray(things, dtype=np.float64).reshape(-1, 20)
     cam = np.ascontiguousarray(cam, dtype=np.float64)
@@ -41,5 +41,37 @@ def render(things, cam, w, h, spp, depth=50, seed=4711, sample0=0, sample_stride
     L.emu_render(_p(things), ctypes.c_int(len(things)), ctypes.c_int(n), vp, _p(nv), ip, _p(nt), _p(cam),
                  ctypes.c_int(w), ctypes.c_int(h), ctypes.c_int(spp), ctypes.c_int(depth), ctypes.c_uint64(seed),
                  ctypes.c_int(sample0), ctypes.c_int(sample_stride), _p(fix), _p(rpp), _p(fid), _p(ft),
-                 ctypes.c_int(1 if brute else 0))
+                 ctypes.c_int(1 if brute else 0), ctypes.c_int(1 if pool else 0))
     return dict(fix=fix, rpp=rpp, first_id=fid, first_t=ft)
+
+
+def stats(reset=True):
+    """Traversal counters of the harness since the last reset."""
+    out = np.zeros(9, dtype=np.uint64)
+    lib().emu_stats(_p(out), ctypes.c_int(1 if reset else 0))
+    names = ["rays", "nodes", "leaves", "tris", "things", "spheres", "enters", "pushes", "max_stack"]
+    return dict(zip(names, [int(v) for v in out]))
+
+
+def trace(things, cam, w, h, spp, depth=50, seed=4711, meshes=None):
+    """Event trace of every path (see emu_trace in hostemu.cu): bytes."""
+    L = lib()
+    L.emu_trace.restype = ctypes.c_longlong
+    things = np.ascontiguousarray(things, dtype=np.float64).reshape(-1, 20)
+    cam = np.ascontiguousarray(cam, dtype=np.float64)
+    meshes = meshes or []
+    v = [np.ascontiguousarray(m[0], dtype=np.float32).reshape(-1, 3) for m in meshes]
+    i = [np.ascontiguousarray(m[1], dtype=np.uint32).reshape(-1, 3) for m in meshes]
+    n = len(meshes)
+    vp = (ctypes.c_void_p * max(n, 1))(*[a.ctypes.data for a in v])
+    ip = (ctypes.c_void_p * max(n, 1))(*[a.ctypes.data for a in i])
+    nv = np.array([len(a) for a in v] or [0], dtype=np.uint32)
+    nt = np.array([len(a) for a in i] or [0], dtype=np.uint32)
+    cap = 64 << 20
+    buf = ctypes.create_string_buffer(cap)
+    got = L.emu_trace(_p(things), ctypes.c_int(len(things)), ctypes.c_int(n), vp, _p(nv), ip, _p(nt), _p(cam),
+                      ctypes.c_int(w), ctypes.c_int(h), ctypes.c_int(spp), ctypes.c_int(depth), ctypes.c_uint64(seed),
+                      buf, ctypes.c_longlong(cap))
+    if got > cap:
+        raise RuntimeError("trace larger than the buffer")
+    return buf.raw[:got]

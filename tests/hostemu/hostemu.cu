@@ -9,11 +9,19 @@
 #include <cstring>
 #include <vector>
 
+#define RTX_STATS 1
 #include "../../rtxplay_b200/csrc/rtx_core.cuh"
 #include "../../rtxplay_b200/csrc/rtx_lbvh.cuh"
+#include "../../rtxplay_b200/csrc/rtx_pool.cuh"
 #include "../../rtxplay_b200/csrc/rtx_hostmath.h"
 
 using namespace rtx ;
+#include <string>
+namespace rtx {
+Stats g_stats = { 0, 0, 0, 0, 0, 0, 0, 0, 0 } ;
+std::string* g_trace = nullptr ;
+void trace_event( char c ) { if ( g_trace ) g_trace->push_back( c ) ; }
+}
 
 namespace {
 
@@ -21,9 +29,36 @@ struct HostStack {
 	int32_t v[256] ; int sp ;
 	RTX_HD void reset() { sp = 0 ; }
 	RTX_HD bool empty() const { return sp == 0 ; }
-	RTX_HD void push( int32_t x ) { v[sp++] = x ; }
+	RTX_HD void push( int32_t x ) { v[sp++] = x ; RTX_COUNT( pushes ) ; RTX_COUNT_MAX( maxsp, sp ) ; }
 	RTX_HD int32_t pop() { return v[--sp] ; }
 } ;
+
+// one ray slot, array backed: the store the step functions of rtx_pool.cuh run on here
+struct HostPool {
+	uint32_t w[F_WORDS] ; int32_t ovf[256] ;
+	RTX_HD float   f( int fld, int ) const { float v ; memcpy( &v, &w[fld], 4 ) ; return v ; }
+	RTX_HD int32_t i( int fld, int ) const { return int32_t( w[fld] ) ; }
+	RTX_HD void    sf( int fld, int, float v ) { memcpy( &w[fld], &v, 4 ) ; }
+	RTX_HD void    si( int fld, int, int32_t v ) { w[fld] = uint32_t( v ) ; }
+	RTX_HD void    push( int, int32_t& sp, int32_t v ) { if ( sp<RTX_POOL_STACK ) w[F_STACK+sp] = uint32_t( v ) ; else ovf[sp-RTX_POOL_STACK] = v ; sp++ ; }
+	RTX_HD int32_t pop( int, int32_t& sp ) { sp-- ; return sp<RTX_POOL_STACK ? int32_t( w[F_STACK+sp] ) : ovf[sp-RTX_POOL_STACK] ; }
+} ;
+
+// a whole path through the state machine of the render kernel
+f3 pool_path( const SceneDev& S, const CameraDev& cam, uint32_t x, uint32_t y, uint32_t w, uint32_t h, uint64_t seed, uint32_t sample, uint32_t depth, uint32_t& segments ) {
+	static HostPool P ;
+	int kind = step_regen( P, 0, S, cam, x, y, w, h, 0u, seed, sample, depth ) ;
+	f3 c = mk3( 0.f, 0.f, 0.f ) ;
+	while ( true ) {
+		switch ( kind ) {
+			case K_NODE:  kind = step_node( P, 0, S ) ; break ;
+			case K_LEAF:  kind = step_leaf( P, 0, S ) ; break ;
+			case K_THING: kind = step_thing( P, 0, S ) ; break ;
+			case K_SHADE: segments++ ; kind = step_shade( P, 0, S, c ) ; break ;
+			default: return c ;
+		}
+	}
+}
 
 struct Tree {
 	std::vector<q4>       nodes ;
@@ -31,8 +66,9 @@ struct Tree {
 	q4 root_lo, root_hi ;
 } ;
 
-// the same pipeline as lbvh_build(), serial: keys -> stable sort -> karras -> refit -> emit
-void build_tree( const std::vector<q4>& plo, const std::vector<q4>& phi, Tree& T ) {
+// the same pipeline as lbvh_build(), serial: keys -> stable sort -> karras -> refit -> collapse
+struct I2 { int x, y ; } ;
+void build_tree( const std::vector<q4>& plo, const std::vector<q4>& phi, Tree& T, int leaf_max ) {
 	const int n = int( plo.size() ) ;
 	float mn[3] = { INFINITY, INFINITY, INFINITY }, mx[3] = { -INFINITY, -INFINITY, -INFINITY } ;
 	for ( int i = 0 ; i<n ; i++ ) {
@@ -58,45 +94,65 @@ void build_tree( const std::vector<q4>& plo, const std::vector<q4>& phi, Tree& T
 		pad_box( lo, hi ) ;
 		blo[n-1+j] = { lo.x, lo.y, lo.z, 0.f } ; bhi[n-1+j] = { hi.x, hi.y, hi.z, 0.f } ;
 	}
-	T.nodes.assign( size_t( n>1 ? n-1 : 1 )*RTX_NODE_RECS, q4{ 0, 0, 0, 0 } ) ;
-	if ( n == 1 ) {
-		const int ref = ~0 ;
-		T.nodes[0] = { blo[0].x, blo[0].y, blo[0].z, asfloat( ref ) } ;
-		T.nodes[1] = { bhi[0].x, bhi[0].y, bhi[0].z, asfloat( ref ) } ;
-		T.nodes[2] = T.nodes[0] ; T.nodes[3] = T.nodes[1] ;
-		T.root_lo = blo[0] ; T.root_hi = bhi[0] ;
-		return ;
-	}
-	std::vector<int> cl( n-1 ), cr( n-1 ) ;
+	std::vector<I2> child( n>1 ? n-1 : 1 ), range( n>1 ? n-1 : 1 ) ;
 	for ( int i = 0 ; i<n-1 ; i++ ) {
-		int l, r ; bool ll, rl ;
-		karras_node( sk.data(), n, i, l, r, ll, rl ) ;
-		cl[i] = ll ? ~l : l ; cr[i] = rl ? ~r : r ;
+		int l, r, lo, hi ; bool ll, rl ;
+		karras_node( sk.data(), n, i, l, r, ll, rl, lo, hi ) ;
+		child[i].x = ll ? ~l : l ; child[i].y = rl ? ~r : r ;
+		range[i].x = lo ; range[i].y = hi ;
 	}
-	// post-order refit without recursion
-	std::vector<int> todo ; std::vector<char> seen( n-1, 0 ) ;
-	todo.push_back( 0 ) ;
-	while ( ! todo.empty() ) {
-		const int i = todo.back() ;
-		if ( ! seen[i] ) {
-			seen[i] = 1 ;
-			if ( cl[i]>=0 ) todo.push_back( cl[i] ) ;
-			if ( cr[i]>=0 ) todo.push_back( cr[i] ) ;
-			continue ;
+	if ( n>1 ) {
+		// post-order refit without recursion
+		std::vector<int> todo ; std::vector<char> seen( n-1, 0 ) ;
+		todo.push_back( 0 ) ;
+		while ( ! todo.empty() ) {
+			const int i = todo.back() ;
+			if ( ! seen[i] ) {
+				seen[i] = 1 ;
+				if ( child[i].x>=0 ) todo.push_back( child[i].x ) ;
+				if ( child[i].y>=0 ) todo.push_back( child[i].y ) ;
+				continue ;
+			}
+			todo.pop_back() ;
+			const int a = child[i].x<0 ? n-1+( ~child[i].x ) : child[i].x, b = child[i].y<0 ? n-1+( ~child[i].y ) : child[i].y ;
+			blo[i] = { fminf( blo[a].x, blo[b].x ), fminf( blo[a].y, blo[b].y ), fminf( blo[a].z, blo[b].z ), 0.f } ;
+			bhi[i] = { fmaxf( bhi[a].x, bhi[b].x ), fmaxf( bhi[a].y, bhi[b].y ), fmaxf( bhi[a].z, bhi[b].z ), 0.f } ;
 		}
-		todo.pop_back() ;
-		const int a = cl[i]<0 ? n-1+( ~cl[i] ) : cl[i], b = cr[i]<0 ? n-1+( ~cr[i] ) : cr[i] ;
-		blo[i] = { fminf( blo[a].x, blo[b].x ), fminf( blo[a].y, blo[b].y ), fminf( blo[a].z, blo[b].z ), 0.f } ;
-		bhi[i] = { fmaxf( bhi[a].x, bhi[b].x ), fmaxf( bhi[a].y, bhi[b].y ), fmaxf( bhi[a].z, bhi[b].z ), 0.f } ;
 	}
-	for ( int i = 0 ; i<n-1 ; i++ ) {
-		const int a = cl[i]<0 ? n-1+( ~cl[i] ) : cl[i], b = cr[i]<0 ? n-1+( ~cr[i] ) : cr[i] ;
-		const int ra = cl[i]<0 ? ~( ( ~cl[i] )<<2 ) : cl[i], rb = cr[i]<0 ? ~( ( ~cr[i] )<<2 ) : cr[i] ;
-		q4* o = T.nodes.data()+size_t( i )*RTX_NODE_RECS ;
-		o[0] = { blo[a].x, blo[a].y, blo[a].z, asfloat( ra ) } ;
-		o[1] = { bhi[a].x, bhi[a].y, bhi[a].z, asfloat( rb ) } ;
-		o[2] = { blo[b].x, blo[b].y, blo[b].z, 0.f } ;
-		o[3] = { bhi[b].x, bhi[b].y, bhi[b].z, 0.f } ;
+	// collapse, breadth first (k_wide_level)
+	std::vector<I2> front( 1, I2{ 0, 0 } ) ;
+	int n_nodes = 1 ;
+	T.nodes.assign( RTX_NODE_RECS, q4{ 0, 0, 0, 0 } ) ;
+	while ( ! front.empty() ) {
+		std::vector<I2> next ;
+		for ( const I2& item : front ) {
+			float lo[3][RTX_WIDTH], hi[3][RTX_WIDTH] ; int ref[RTX_WIDTH] ;
+			for ( int k = 0 ; k<RTX_WIDTH ; k++ ) { ref[k] = RTX_REF_EMPTY ; for ( int a = 0 ; a<3 ; a++ ) { lo[a][k] = 0.f ; hi[a][k] = 0.f ; } }
+			if ( n == 1 ) {
+				ref[0] = ~0 ;
+				lo[0][0] = blo[0].x ; lo[1][0] = blo[0].y ; lo[2][0] = blo[0].z ; hi[0][0] = bhi[0].x ; hi[1][0] = bhi[0].y ; hi[2][0] = bhi[0].z ;
+			} else {
+				int slots[RTX_WIDTH] ;
+				const int ns = wide_gather( item.x, child.data(), range.data(), blo.data(), bhi.data(), n, leaf_max, slots ) ;
+				for ( int k = 0 ; k<ns ; k++ ) {
+					const int s = slots[k] ;
+					const int b = s<0 ? n-1+( ~s ) : s ;
+					lo[0][k] = blo[b].x ; lo[1][k] = blo[b].y ; lo[2][k] = blo[b].z ; hi[0][k] = bhi[b].x ; hi[1][k] = bhi[b].y ; hi[2][k] = bhi[b].z ;
+					if ( ! wide_leaf_ref( s, range.data(), leaf_max, ref[k] ) ) {
+						ref[k] = n_nodes++ ;
+						next.push_back( I2{ s, ref[k] } ) ;
+					}
+				}
+			}
+			if ( T.nodes.size()<size_t( n_nodes )*RTX_NODE_RECS ) T.nodes.resize( size_t( n_nodes )*RTX_NODE_RECS, q4{ 0, 0, 0, 0 } ) ;
+			q4* o = T.nodes.data()+size_t( item.y )*RTX_NODE_RECS ;
+			for ( int a = 0 ; a<3 ; a++ ) {
+				o[a]   = { lo[a][0], lo[a][1], lo[a][2], lo[a][3] } ;
+				o[3+a] = { hi[a][0], hi[a][1], hi[a][2], hi[a][3] } ;
+			}
+			o[6] = { asfloat( ref[0] ), asfloat( ref[1] ), asfloat( ref[2] ), asfloat( ref[3] ) } ;
+		}
+		front.swap( next ) ;
 	}
 	T.root_lo = blo[0] ; T.root_hi = bhi[0] ;
 }
@@ -125,7 +181,7 @@ void build_scene( EmuScene& E, const double* things, int n_things, int n_meshes,
 			plo[f] = { fminf( a[0], fminf( b[0], c[0] ) ), fminf( a[1], fminf( b[1], c[1] ) ), fminf( a[2], fminf( b[2], c[2] ) ), 0.f } ;
 			phi[f] = { fmaxf( a[0], fmaxf( b[0], c[0] ) ), fmaxf( a[1], fmaxf( b[1], c[1] ) ), fmaxf( a[2], fmaxf( b[2], c[2] ) ), 0.f } ;
 		}
-		build_tree( plo, phi, m.tree ) ;
+		build_tree( plo, phi, m.tree, RTX_LEAF_MAX ) ;
 		m.tris.resize( 3*size_t( nt[q] ) ) ;
 		for ( uint32_t j = 0 ; j<nt[q] ; j++ ) {
 			const uint32_t f = m.tree.order[j] ;
@@ -168,7 +224,7 @@ void build_scene( EmuScene& E, const double* things, int n_things, int n_meshes,
 			phi[k] = { float( mx[0] )+1e-3f, float( mx[1] )+1e-3f, float( mx[2] )+1e-3f, 0.f } ;
 		}
 	}
-	if ( n_things ) build_tree( plo, phi, E.tlas ) ;
+	if ( n_things ) build_tree( plo, phi, E.tlas, 1 ) ;
 	E.S.tlas_nodes = E.tlas.nodes.data() ; E.S.tlas_order = E.tlas.order.data() ;
 	E.S.trav = E.trav.data() ; E.S.shade = E.shade.data() ; E.S.n_things = uint32_t( n_things ) ;
 }
@@ -180,7 +236,7 @@ extern "C" {
 // cam: 19 doubles (eye,u,v,hvec,wvec,dvec,aperture) as in the oracle tables
 int emu_render( const double* things, int n_things, int n_meshes, const float* const* vces, const uint32_t* nv, const uint32_t* const* ices, const uint32_t* nt,
 		const double* cam, int w, int h, int spp, int depth, uint64_t seed, int sample0, int sample_stride,
-		uint64_t* fix, uint32_t* rpp, int64_t* first_id, float* first_t, int brute ) {
+		uint64_t* fix, uint32_t* rpp, int64_t* first_id, float* first_t, int brute, int use_pool ) {
 	EmuScene E ;
 	build_scene( E, things, n_things, n_meshes, vces, nv, ices, nt ) ;
 	CameraDev c ;
@@ -205,13 +261,65 @@ int emu_render( const double* things, int n_things, int n_meshes, const float* c
 					first_id[pix] = hr.thing<0 ? int64_t( -1 ) : ( ( int64_t( hr.thing )<<32 )|int64_t( uint32_t( hr.prim+1 ) ) ) ;
 					if ( first_t ) first_t[pix] = hr.thing<0 ? -1.f : hr.t ;
 				}
-				const f3 col = path_radiance( E.S, ori, dir, uint32_t( depth ), rng, st, segments ) ;
+				const f3 col = use_pool ? pool_path( E.S, c, uint32_t( x ), uint32_t( y ), uint32_t( w ), uint32_t( h ), seed, uint32_t( sample0+k*sample_stride ), uint32_t( depth ), segments )
+				                        : path_radiance( E.S, ori, dir, uint32_t( depth ), rng, st, segments ) ;
 				acc[0] += tofix( col.x ) ; acc[1] += tofix( col.y ) ; acc[2] += tofix( col.z ) ;
 			}
 			if ( fix ) { fix[3*size_t( pix )] = acc[0] ; fix[3*size_t( pix )+1] = acc[1] ; fix[3*size_t( pix )+2] = acc[2] ; }
 			if ( rpp ) rpp[pix] = segments ;
 		}
 	return 0 ;
+}
+
+// event trace of every path of an image: per pixel (row-major) and sample, the traversal
+// events of its rays ('N' node, '1'..'4' leaf with that many triangles, 'P' sphere test,
+// 'E' enter mesh, 'R' return) with '|' after each ray and ';' after each path
+long long emu_trace( const double* things, int n_things, int n_meshes, const float* const* vces, const uint32_t* nv, const uint32_t* const* ices, const uint32_t* nt,
+		const double* cam, int w, int h, int spp, int depth, uint64_t seed, char* out, long long cap ) {
+	EmuScene E ;
+	build_scene( E, things, n_things, n_meshes, vces, nv, ices, nt ) ;
+	CameraDev c ;
+	c.eye = mk3( float( cam[0] ), float( cam[1] ), float( cam[2] ) ) ; c.u = mk3( float( cam[3] ), float( cam[4] ), float( cam[5] ) ) ;
+	c.v = mk3( float( cam[6] ), float( cam[7] ), float( cam[8] ) ) ; c.hvec = mk3( float( cam[9] ), float( cam[10] ), float( cam[11] ) ) ;
+	c.wvec = mk3( float( cam[12] ), float( cam[13] ), float( cam[14] ) ) ; c.dvec = mk3( float( cam[15] ), float( cam[16] ), float( cam[17] ) ) ;
+	c.aperture = float( cam[18] ) ;
+	std::string tr ;
+	g_trace = &tr ;
+	HostStack st ;
+	for ( int y = 0 ; y<h ; y++ )
+		for ( int x = 0 ; x<w ; x++ ) {
+			const uint32_t pix = uint32_t( w )*y+x ;
+			for ( int k = 0 ; k<spp ; k++ ) {
+				Pcg rng ;
+				rng.seed( seed, pix, uint32_t( k ) ) ;
+				f3 ori, dir ;
+				primary_ray( c, uint32_t( x ), uint32_t( y ), uint32_t( w ), uint32_t( h ), rng, ori, dir ) ;
+				// path_radiance, with a ray separator
+				f3 thr = mk3( 1.f, 1.f, 1.f ) ; uint32_t dl = uint32_t( depth ) ;
+				while ( true ) {
+					HitRec hr ;
+					closest( E.S, ori, dir, 1e-3f, st, hr ) ;
+					tr.push_back( '|' ) ;
+					if ( hr.thing<0 || dl == 0 ) break ;
+					Frame fr ; frame_of( E.S, hr, ori, dir, 1e-3f, fr ) ;
+					f3 att, out2 ;
+					if ( ! scatter( E.S.shade+hr.thing, dir, fr, rng, att, out2 ) ) break ;
+					thr = thr*att ; ori = fr.p ; dir = out2 ; dl-- ;
+				}
+				tr.push_back( ';' ) ;
+			}
+		}
+	g_trace = nullptr ;
+	const long long n = ( long long ) tr.size() ;
+	if ( out && n<=cap ) memcpy( out, tr.data(), size_t( n ) ) ;
+	return n ;
+}
+
+// traversal counters since the last reset: rays, nodes, leaves, tris, things, spheres, enters, pushes, max stack
+void emu_stats( unsigned long long* out, int reset ) {
+	const unsigned long long v[9] = { g_stats.rays, g_stats.nodes, g_stats.leaves, g_stats.tris, g_stats.things, g_stats.spheres, g_stats.enters, g_stats.pushes, g_stats.maxsp } ;
+	for ( int k = 0 ; k<9 ; k++ ) out[k] = v[k] ;
+	if ( reset ) g_stats = Stats{ 0, 0, 0, 0, 0, 0, 0, 0, 0 } ;
 }
 
 } // extern "C"

@@ -92,8 +92,9 @@ def test_scene_generator_shape():
     assert [s["ndiv"] for s in sp[-3:]] == [8, 6, 3]
 
 
+@pytest.mark.parametrize("pool", [True, False])
 @pytest.mark.parametrize("mode,ndiv", [("analytic", None), ("mesh", 2)])
-def test_cuda_core_on_host_equals_float_mirror(mode, ndiv):
+def test_cuda_core_on_host_equals_float_mirror(mode, ndiv, pool):
     """The __host__ __device__ core (traversal through a Karras LBVH, primitive tests, shading,
     random stream) == oracle<float>: fixed-point radiance, segments and first-hit ids, bit for bit."""
     sp = scenes.book1(seed=3)
@@ -101,7 +102,9 @@ def test_cuda_core_on_host_equals_float_mirror(mode, ndiv):
     cam = api.camera_table(api.camera(aspratio=1.5))
     w, h, spp = 60, 40, 2
     f = orc.render(orc.F32_PCG, tab, cam, w, h, spp, 50, want_first=True, meshes=meshes)
-    e = hostemu.render(tab, cam, w, h, spp, 50, meshes=meshes)
+    # pool=True: the step functions of the render kernel's state machine (rtx_pool.cuh);
+    # pool=False: the single-ray traversal used by the picker and the parity instruments
+    e = hostemu.render(tab, cam, w, h, spp, 50, meshes=meshes, pool=pool)
     assert np.array_equal(f["first_id"], e["first_id"])
     assert np.array_equal(f["rpp"], e["rpp"])
     assert np.array_equal(f["fix"], e["fix"])
