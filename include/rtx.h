@@ -74,7 +74,8 @@ enum {
 	RTX_BUF_HIT_ID  = 4,  /* int64[w*h]    first-hit id of rtx_primary_hits: thing<<32 | prim+1, -1 = miss */
 	RTX_BUF_HIT_T   = 5,  /* float[w*h]    its ray parameter */
 	RTX_BUF_NORMALS = 6,  /* float[3*w*h]  LpGeneral.normals (optx/launcher.cxx:43) */
-	RTX_BUF_ALBEDOS = 7   /* float[3*w*h]  LpGeneral.albedos (optx/launcher.cxx:44) */
+	RTX_BUF_ALBEDOS = 7,  /* float[3*w*h]  LpGeneral.albedos (optx/launcher.cxx:44) */
+	RTX_BUF_PICK_ID = 8   /* uint32[1]     LpGeneral.pick_id (optx/launcher.cxx:46), written by rtx_pick */
 } ;
 
 enum { RTX_PP_NONE = 0, RTX_PP_SRGB = 1 } ;

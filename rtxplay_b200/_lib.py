@@ -5,7 +5,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "librtx.so")
+_SO = os.environ.get("RTX_LIB") or os.path.join(_HERE, "librtx.so")   # RTX_LIB: an experimental build
 _LIB = None
 
 

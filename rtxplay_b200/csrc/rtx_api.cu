@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -18,6 +19,10 @@
 #include "rtx_hostmath.h"
 
 using namespace rtx ;
+
+#ifndef RTX_DEFAULT_CARVEOUT
+#define RTX_DEFAULT_CARVEOUT 50
+#endif
 
 static_assert( sizeof( ThingTrav ) == 128, "ThingTrav layout" ) ;
 static_assert( sizeof( ThingShade ) == 144, "ThingShade layout" ) ;
@@ -351,6 +356,7 @@ BufInfo buffer_of( rtx_ctx* c, int buffer ) {
 		case RTX_BUF_HIT_T:   return { c->d_hit_t,   np*sizeof( float ) } ;
 		case RTX_BUF_NORMALS: return { c->d_normals, np*3*sizeof( float ) } ;
 		case RTX_BUF_ALBEDOS: return { c->d_albedos, np*3*sizeof( float ) } ;
+		case RTX_BUF_PICK_ID: return { c->d_pick,    sizeof( uint32_t ) } ;
 	}
 	throw std::runtime_error( "rtx: unknown buffer id" ) ;
 }
@@ -394,6 +400,12 @@ int rtx_init( int device, rtx_ctx** out ) {
 		c->d_counter = dalloc<unsigned long long>( c, 1 ) ;
 		c->d_tile_counter = dalloc<uint32_t>( c, 1 ) ;
 		// the render kernel is persistent: one warp per CTA, as many CTAs as fit
+		// shared memory holds the ray slots, L1 caches the BVH: the carveout decides how many
+		// render warps an SM hosts and how much L1 is left (tunable: RTX_CARVEOUT, percent)
+		int carve = RTX_DEFAULT_CARVEOUT ;
+		if ( const char* e = getenv( "RTX_CARVEOUT" ) ) carve = atoi( e ) ;
+		if ( carve>0 && carve<=100 )
+			CK( cudaFuncSetAttribute( k_render, cudaFuncAttributePreferredSharedMemoryCarveout, carve ) ) ;
 		int per_sm = 0 ;
 		CK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm, k_render, 32, 0 ) ) ;
 		if ( per_sm<1 ) per_sm = 1 ;

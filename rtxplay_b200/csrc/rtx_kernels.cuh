@@ -69,14 +69,21 @@ inline uint32_t tile_grid( uint32_t w, uint32_t h ) {
 // fixed-point sums.  Tiles are handed out through a global counter.
 #define RTX_POOL_R ( 32*RTX_K )
 __global__ void __launch_bounds__( 32 ) k_render( const FrameArgs a, uint32_t* tile_counter, int32_t* ovf_all ) {
-	__shared__ uint32_t words[F_WORDS*RTX_POOL_R] ;
 	__shared__ unsigned long long acc[32*3] ;
 	__shared__ uint32_t segs[32] ;
 	const uint32_t lane = threadIdx.x ;
 	const uint32_t lt = ( 1u<<lane )-1u ;
+#if defined( RTX_REGPOOL )
+	__shared__ uint32_t stack_words[RTX_POOL_STACK*32] ;
+	RegPool p ;
+	p.stk = stack_words+lane ;
+	p.ovf = ovf_all+( size_t( blockIdx.x )*RTX_POOL_R+lane )*RTX_POOL_OVF ;
+#else
+	__shared__ uint32_t words[F_WORDS*RTX_POOL_R] ;
 	DevPool p ;
 	p.w = words ;
 	p.ovf = ovf_all+size_t( blockIdx.x )*RTX_POOL_R*RTX_POOL_OVF ;
+#endif
 	const uint32_t tiles_x = ( a.w+7u )>>3, tiles_y = ( a.h+3u )>>2, n_tiles = tiles_x*tiles_y ;
 
 	while ( true ) {

@@ -69,6 +69,31 @@ struct DevPool {
 } ;
 #endif
 
+#if defined( __CUDACC__ )
+// one ray per lane, state in registers (every field index is a compile-time constant), only
+// the stack in shared memory: no shared-memory traffic for the state, no limit on resident
+// warps from it, at the price of fewer candidate rays per vote (RTX_K must be 1)
+struct RegPool {
+	uint32_t  r[F_STACK] ;
+	uint32_t* stk ;    // this lane's stack column in shared memory, stride 32
+	int32_t*  ovf ;
+	__device__ __forceinline__ float    f( int fld, int ) const { return __uint_as_float( r[fld] ) ; }
+	__device__ __forceinline__ int32_t  i( int fld, int ) const { return int32_t( r[fld] ) ; }
+	__device__ __forceinline__ void     sf( int fld, int, float v ) { r[fld] = __float_as_uint( v ) ; }
+	__device__ __forceinline__ void     si( int fld, int, int32_t v ) { r[fld] = uint32_t( v ) ; }
+	__device__ __forceinline__ void     push( int, int32_t& sp, int32_t v ) {
+		if ( sp<RTX_POOL_STACK ) stk[sp*32] = uint32_t( v ) ;
+		else if ( sp<RTX_POOL_STACK+RTX_POOL_OVF ) ovf[sp-RTX_POOL_STACK] = v ;
+		sp++ ;
+	}
+	__device__ __forceinline__ int32_t  pop( int, int32_t& sp ) {
+		sp-- ;
+		if ( sp<RTX_POOL_STACK ) return int32_t( stk[sp*32] ) ;
+		return sp<RTX_POOL_STACK+RTX_POOL_OVF ? ovf[sp-RTX_POOL_STACK] : RTX_STK_DONE ;
+	}
+} ;
+#endif
+
 template <class P> RTX_HD f3 ld3( const P& p, int fld, int slot ) { return mk3( p.f( fld, slot ), p.f( fld+1, slot ), p.f( fld+2, slot ) ) ; }
 template <class P> RTX_HD void st3( P& p, int fld, int slot, const f3& v ) { p.sf( fld, slot, v.x ) ; p.sf( fld+1, slot, v.y ) ; p.sf( fld+2, slot, v.z ) ; }
 template <class P, class T> RTX_HD const T* ldp( const P& p, int fld, int slot ) {

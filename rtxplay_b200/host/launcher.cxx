@@ -8,6 +8,7 @@
 
 namespace cg {
 	extern LpGeneral lp_general ;
+	extern rtx_ctx*  rtx_context ;  // postproc.cxx: the context pp_none / pp_sRGB run on
 }
 using namespace cg ;
 
@@ -16,10 +17,12 @@ Launcher::Launcher( const OptixPipeline& /*pipeline*/, const OptixShaderBindingT
 	ctx_ = reinterpret_cast<rtx_ctx*>( lp_general.is_handle ) ;
 	if ( ! ctx_ )
 		throw std::runtime_error( "Launcher: build the scene before creating the launcher\n" ) ;
+	rtx_context = ctx_ ;
 	resize( lp_general.image_w, lp_general.image_h ) ;
 }
 
 Launcher::Launcher( const OptixDeviceContext& optx_context ) : ctx_( optx_context ), seed_( 4711 ) {
+	rtx_context = ctx_ ;
 	resize( lp_general.image_w, lp_general.image_h ) ;
 }
 

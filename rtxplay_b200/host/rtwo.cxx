@@ -1,0 +1,230 @@
+// rtwo.cxx -- the batch driver of RTWO (flow of optx/rtwo.cxx:78-620 without OptiX, the
+// viewer and the denoiser): options -> launch parameters -> scene recipe -> acceleration
+// structures -> one frame -> post-processing -> PPM (and AOVs) on stdout, -S statistics on
+// stderr.  Exits 1 with "exception: ..." on any failure, like the reference.
+#include <chrono>
+#include <cstdio>
+#include <iostream>
+#include <vector>
+
+#include "args.h"
+#include "launcher.h"
+#include "rtwo.h"
+#include "scene.h"
+#include "sphere.h"
+#include "util.h"
+#include "v.h"
+
+// common globals (optx/rtwo.cxx:30-36)
+namespace cg {
+	Args*     args ;
+	Scene*    scene ;
+	LpGeneral lp_general ;
+	Launcher* launcher ;
+}
+using cg::lp_general ;
+
+using V::operator- ;
+using V::operator* ;
+
+// post processing (postproc.cxx)
+extern "C" void pp_none( const float3* src, uchar4* dst, const int w, const int h ) ;
+extern "C" void pp_sRGB( const float3* src, uchar4* dst, const int w, const int h ) ;
+
+#define MAX_DEPTH 50
+
+// ---- image output: text PNM, rows flipped so that y points up (optx/rtwo.cxx:622-666)
+static void imgtopnm( const std::vector<uchar4>& rgb, const int w, const int h ) {
+	printf( "P3\n%d %d\n255\n", w, h ) ;
+	for ( int y = h-1 ; y>=0 ; --y )
+		for ( int x = 0 ; x<w ; ++x ) {
+			const uchar4 p = rgb[size_t( w )*y+x] ;
+			printf( "%d %d %d\n", int( p.x ), int( p.y ), int( p.z ) ) ;
+		}
+	printf( "\n" ) ;
+}
+static void imgtopnm( const std::vector<float3>& rgb, const int w, const int h ) {
+	printf( "P3\n%d %d\n255\n", w, h ) ;
+	for ( int y = h-1 ; y>=0 ; --y )
+		for ( int x = 0 ; x<w ; ++x ) {
+			const float3 p = rgb[size_t( w )*y+x] ;
+			printf( "%d %d %d\n", int( util::clamp( p.x, 0.f, 1.f )*255 ), int( util::clamp( p.y, 0.f, 1.f )*255 ), int( util::clamp( p.z, 0.f, 1.f )*255 ) ) ;
+		}
+	printf( "\n" ) ;
+}
+static void imgtopnm( const std::vector<unsigned int>& mono, const int w, const int h ) {
+	printf( "P2\n%d %d\n65535\n", w, h ) ;
+	for ( int y = h-1 ; y>=0 ; --y )
+		for ( int x = 0 ; x<w ; ++x )
+			printf( "%u\n", mono[size_t( w )*y+x] ) ;
+	printf( "\n" ) ;
+}
+template <typename T> static void imgtopnm( const void* dev ) {
+	const unsigned int w = lp_general.image_w, h = lp_general.image_h ;
+	std::vector<T> image( size_t( w )*h ) ;
+	CUDA_CHECK( cudaMemcpy( image.data(), dev, sizeof( T )*w*h, cudaMemcpyDeviceToHost ) ) ;
+	imgtopnm( image, w, h ) ;
+}
+
+// ---- the scene of the book's cover (optx/rtwo.cxx:133-245), as a user of the Scene API
+class RTWO : public Scene {
+	public:
+		RTWO( const OptixDeviceContext& optx_context, bool analytic ) : Scene( optx_context ), analytic_( analytic ) {} ;
+
+		unsigned int load() override {
+			unsigned int gas_3, gas_6, gas_8, gas_9 ;
+			if ( analytic_ )
+				gas_3 = gas_6 = gas_8 = gas_9 = addAnalyticSphere() ;
+			else {
+				// the reference reads sphere_{3,6,8,9}.scn written by its `sphere` tool; the
+				// same meshes are produced in memory here (Object also reads .scn files)
+				Sphere s3( 1.f, 3 ), s6( 1.f, 6 ), s8( 1.f, 8 ), s9( 1.f, 9 ) ;
+				Object sphere_3( s3.mesh() ), sphere_6( s6.mesh() ), sphere_8( s8.mesh() ), sphere_9( s9.mesh() ) ;
+				gas_3 = add( sphere_3 ) ; gas_6 = add( sphere_6 ) ; gas_8 = add( sphere_8 ) ; gas_9 = add( sphere_9 ) ;
+			}
+
+			Thing thing = {} ;
+			unsigned int id = 0 ;
+			auto place = [&]( unsigned int gas, float scale, float x, float y, float z ) {
+				const float transform[12] = { scale, 0.f, 0.f, x,  0.f, scale, 0.f, y,  0.f, 0.f, scale, z } ;
+				id = add( thing, gas ) ;
+				set( id, transform ) ;
+			} ;
+
+			thing.optics.type = Optics::TYPE_DIFFUSE ;
+			thing.optics.diffuse.albedo = { .5f, .5f, .5f } ;
+			place( gas_9, 1000.f, 0.f, -1000.f, 0.f ) ;
+
+			for ( int a = -11 ; a<11 ; a++ )
+				for ( int b = -11 ; b<11 ; b++ ) {
+					const float select = util::rnd() ;
+					const float cx = a+.9f*util::rnd() ;
+					const float cz = b+.9f*util::rnd() ;
+					const float3 center = { cx, .2f, cz } ;
+					if ( V::len( center-make_float3( 4.f, .2f, 0.f ) )>.9f ) {
+						if ( select<.8f ) {
+							thing.optics.type = Optics::TYPE_DIFFUSE ;
+							const float3 p = V::rnd(), q = V::rnd() ;
+							thing.optics.diffuse.albedo = p*q ;
+							place( gas_6, .2f, center.x, center.y, center.z ) ;
+						} else if ( select<.95f ) {
+							thing.optics.type = Optics::TYPE_REFLECT ;
+							thing.optics.reflect.albedo = V::rnd( .5f, 1.f ) ;
+							thing.optics.reflect.fuzz = util::rnd( 0.f, .5f ) ;
+							place( gas_6, .2f, center.x, center.y, center.z ) ;
+						} else {
+							thing.optics.type = Optics::TYPE_REFRACT ;
+							thing.optics.refract.index = 1.5f ;
+							place( gas_3, .2f, center.x, center.y, center.z ) ;
+						}
+					}
+				}
+
+			thing.optics.type = Optics::TYPE_REFRACT ;
+			thing.optics.refract.index = 1.5f ;
+			place( gas_8, 1.f, 0.f, 1.f, 0.f ) ;
+
+			thing.optics.type = Optics::TYPE_DIFFUSE ;
+			thing.optics.diffuse.albedo = { .4f, .2f, .1f } ;
+			place( gas_6, 1.f, -4.f, 1.f, 0.f ) ;
+
+			thing.optics.type = Optics::TYPE_REFLECT ;
+			thing.optics.reflect.albedo = { .7f, .6f, .5f } ;
+			thing.optics.reflect.fuzz = 0.f ;
+			place( gas_3, 1.f, 4.f, 1.f, 0.f ) ;
+
+			return id+1 ;
+		}
+
+	private:
+		bool analytic_ ;
+} ;
+
+int main( int argc, char* argv[] ) {
+	Args args( argc, argv ) ;
+	cg::args = &args ;
+
+	if ( args.flag_h() ) {
+		Args::usage() ;
+		return 0 ;
+	}
+
+	lp_general.image_w = args.param_w( 1280 ) ; // image width in pixels
+	lp_general.image_h = args.param_h( 720 )  ; // image height in pixels
+	lp_general.spp     = args.param_s( 50 )   ; // samples per pixel
+	const int depth    = args.param_d( MAX_DEPTH ) ;
+	lp_general.depth   = depth>MAX_DEPTH ? MAX_DEPTH : depth ;
+
+	const float aspratio = static_cast<float>( lp_general.image_w )/static_cast<float>( lp_general.image_h ) ;
+	lp_general.camera.set(
+		{ 13.f, 2.f, 3.f } /*eye*/, { 0.f, 0.f, 0.f } /*pat*/, { 0.f, 1.f, 0.f } /*vup*/,
+		20.f /*fov*/, aspratio, .1f /*aperture*/, 10.f /*focus distance*/ ) ;
+
+	rtx_ctx* context = nullptr ;
+	try {
+		if ( rtx_init( args.param_device( 0 ), &context ) != 0 )
+			throw std::runtime_error( std::string( "RTX error: rtx_init : " )+rtx_last_error( nullptr )+"\n" ) ;
+
+		// scene + acceleration structures
+		RTWO rtwo( context, args.flag_analytic() ) ;
+		cg::scene = &rtwo ;
+		const unsigned int rtwo_size = rtwo.load() ;
+		rtwo.build( &lp_general.is_handle ) ;
+		if ( args.flag_v() ) {
+			rtx_stats st ;
+			RTX_CHECK( context, rtx_stats_get( context, &st ) ) ;
+			fprintf( stderr, "rtwo: %u things, %u meshes, %llu triangles stored, %llu instanced; build %.2f ms (meshes) + %.2f ms (top level); %.1f MB on device\n",
+				rtwo_size, st.n_meshes, ( unsigned long long ) st.n_triangles, ( unsigned long long ) st.n_triangles_instanced, st.ms_build_blas, st.ms_build_tlas, st.bytes_device/1048576. ) ;
+		}
+
+		OptixPipeline pipeline = nullptr ;
+		OptixShaderBindingTable sbt ;
+		Launcher launcher( pipeline, sbt ) ;
+		cg::launcher = &launcher ;
+
+		// launch (the reference times ignite + stream destroy, optx/rtwo.cxx:542-546)
+		CUstream cuda_stream ;
+		CUDA_CHECK( cudaStreamCreate( &cuda_stream ) ) ;
+		auto t0 = std::chrono::high_resolution_clock::now() ;
+		launcher.ignite( cuda_stream ) ;
+		CUDA_CHECK( cudaStreamDestroy( cuda_stream ) ) ;
+		auto t1 = std::chrono::high_resolution_clock::now() ;
+
+		const Dns type = args.param_D( Dns::NONE ) ;
+		if ( type != Dns::NONE ) {
+			std::cerr << "rtwo: the OptiX AI denoiser is not part of this build; image left as rendered" << std::endl ;
+			if ( ! args.flag_q() && args.flag_G() ) {
+				if ( lp_general.normals ) imgtopnm<float3>( lp_general.normals ) ;
+				if ( lp_general.albedos ) imgtopnm<float3>( lp_general.albedos ) ;
+			}
+		}
+
+		// post processing
+		const unsigned int w = lp_general.image_w, h = lp_general.image_h ;
+		CUDA_CHECK( cudaMalloc( reinterpret_cast<void**>( &lp_general.image ), sizeof( uchar4 )*w*h ) ) ;
+		pp_sRGB( lp_general.rawRGB, lp_general.image, w, h ) ;
+
+		if ( ! args.flag_q() )
+			imgtopnm<uchar4>( lp_general.image ) ;
+		CUDA_CHECK( cudaFree( lp_general.image ) ) ;
+
+		if ( ! args.flag_q() && args.flag_A( Aov::RPP ) )
+			imgtopnm<unsigned int>( lp_general.rpp ) ;
+
+		if ( args.flag_S() ) {
+			std::vector<unsigned int> rpp( size_t( w )*h ) ;
+			CUDA_CHECK( cudaMemcpy( rpp.data(), lp_general.rpp, sizeof( unsigned int )*w*h, cudaMemcpyDeviceToHost ) ) ;
+			long long dt = std::chrono::duration_cast<std::chrono::milliseconds>( t1-t0 ).count() ;
+			long long sr = 0 ; for ( auto const& c : rpp ) sr = sr+c ;
+			fprintf( stderr, "%9u %12llu %4llu (pixel, rays, milliseconds) %6.2f fps\n", w*h, sr, dt, 1000.f/dt ) ;
+		}
+
+		cg::launcher = nullptr ;
+		rtx_shutdown( context ) ;
+	} catch ( const std::exception& e ) {
+		std::cerr << "exception: " << e.what() << "\n" ;
+		return 1 ;
+	}
+
+	return 0 ;
+}

@@ -5,6 +5,7 @@
 #ifndef RTWO_H
 #define RTWO_H
 
+#include <cuda_runtime.h>
 #include <vector_types.h>
 
 #include "../../include/rtx.h"
