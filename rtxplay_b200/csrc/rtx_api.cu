@@ -410,7 +410,7 @@ int rtx_init( int device, rtx_ctx** out ) {
 		CK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm, k_render, 32, 0 ) ) ;
 		if ( per_sm<1 ) per_sm = 1 ;
 		c->render_grid = uint32_t( per_sm )*uint32_t( prop.multiProcessorCount ) ;
-		c->d_ovf = dalloc<int32_t>( c, size_t( c->render_grid )*RTX_POOL_R*RTX_POOL_OVF ) ;
+		c->d_ovf = dalloc<int32_t>( c, size_t( c->render_grid )*RTX_POOL_R*RTX_POOL_OVF*2 ) ;
 		*out = c ;
 		return 0 ;
 	} catch ( const std::exception& e ) {
@@ -435,7 +435,7 @@ void rtx_shutdown( rtx_ctx* c ) {
 	dfree( c, c->d_tp_lo, c->n_things_dev ) ; dfree( c, c->d_tp_hi, c->n_things_dev ) ;
 	free_frame( c ) ;
 	dfree( c, c->d_pick, 1 ) ; dfree( c, c->d_counter, 1 ) ; dfree( c, c->d_tile_counter, 1 ) ;
-	dfree( c, c->d_ovf, size_t( c->render_grid )*RTX_POOL_R*RTX_POOL_OVF ) ;
+	dfree( c, c->d_ovf, size_t( c->render_grid )*RTX_POOL_R*RTX_POOL_OVF*2 ) ;
 	cudaEventDestroy( c->ev0 ) ; cudaEventDestroy( c->ev1 ) ;
 	cudaStreamDestroy( c->stream ) ;
 	delete c ;

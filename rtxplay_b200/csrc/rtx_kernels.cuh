@@ -68,21 +68,27 @@ inline uint32_t tile_grid( uint32_t w, uint32_t h ) {
 // tile, traces all its paths -- 32*spp of them, RTX_K*32 in flight -- and writes the tile's
 // fixed-point sums.  Tiles are handed out through a global counter.
 #define RTX_POOL_R ( 32*RTX_K )
-__global__ void __launch_bounds__( 32 ) k_render( const FrameArgs a, uint32_t* tile_counter, int32_t* ovf_all ) {
+#ifndef RTX_STICKY
+#define RTX_STICKY 14          // keep doing node steps while at least this many lanes have one
+#endif
+#ifndef RTX_MIN_CTAS
+#define RTX_MIN_CTAS 20         // resident render warps per SM the register budget is set for (96 registers)
+#endif
+__global__ void __launch_bounds__( 32, RTX_MIN_CTAS ) k_render( const FrameArgs a, uint32_t* tile_counter, int32_t* ovf_all ) {
 	__shared__ unsigned long long acc[32*3] ;
 	__shared__ uint32_t segs[32] ;
 	const uint32_t lane = threadIdx.x ;
 	const uint32_t lt = ( 1u<<lane )-1u ;
 #if defined( RTX_REGPOOL )
-	__shared__ uint32_t stack_words[RTX_POOL_STACK*32] ;
+	__shared__ uint32_t stack_words[2*RTX_POOL_STACK*32] ;
 	RegPool p ;
 	p.stk = stack_words+lane ;
-	p.ovf = ovf_all+( size_t( blockIdx.x )*RTX_POOL_R+lane )*RTX_POOL_OVF ;
+	p.ovf = ovf_all+( size_t( blockIdx.x )*RTX_POOL_R+lane )*RTX_POOL_OVF*2 ;
 #else
 	__shared__ uint32_t words[F_WORDS*RTX_POOL_R] ;
 	DevPool p ;
 	p.w = words ;
-	p.ovf = ovf_all+size_t( blockIdx.x )*RTX_POOL_R*RTX_POOL_OVF ;
+	p.ovf = ovf_all+size_t( blockIdx.x )*RTX_POOL_R*RTX_POOL_OVF*2 ;
 #endif
 	const uint32_t tiles_x = ( a.w+7u )>>3, tiles_y = ( a.h+3u )>>2, n_tiles = tiles_x*tiles_y ;
 
@@ -105,6 +111,12 @@ __global__ void __launch_bounds__( 32 ) k_render( const FrameArgs a, uint32_t* t
 
 		while ( true ) {
 			// vote: which step kind can most lanes take?
+#if RTX_K == 1
+			// one ray per lane: lanes of equal kind find each other (match), the largest group
+			// wins (warp-wide max of size<<3|kind)
+			const uint32_t peers = __match_any_sync( 0xffffffffu, kinds[0] ) ;
+			const int kind = int( __reduce_max_sync( 0xffffffffu, kinds[0] == K_DONE ? 0u : ( uint32_t( __popc( peers ) )<<3 )|uint32_t( kinds[0] ) )&7u ) ;
+#else
 			uint32_t mine = 0 ;
 #pragma unroll
 			for ( int j = 0 ; j<RTX_K ; j++ ) mine |= 1u<<kinds[j] ;
@@ -114,6 +126,7 @@ __global__ void __launch_bounds__( 32 ) k_render( const FrameArgs a, uint32_t* t
 				const int n = __popc( __ballot_sync( 0xffffffffu, ( mine>>k )&1u ) ) ;
 				if ( n>most ) { most = n ; kind = k ; }
 			}
+#endif
 			if ( kind == K_DONE )
 				break ;
 			int j = -1 ;
@@ -122,9 +135,25 @@ __global__ void __launch_bounds__( 32 ) k_render( const FrameArgs a, uint32_t* t
 			const int slot = j*32+int( lane ) ;
 			int nk = kind ;
 			switch ( kind ) {
-				case K_NODE:
-					if ( j>=0 ) nk = step_node( p, slot, a.S ) ;
+				case K_NODE: {
+					// node steps dominate: stay with them (one ballot per step instead of a full
+					// vote) while enough lanes still have one
+					int jn = j ;
+					while ( true ) {
+						if ( jn>=0 ) {
+							const int kn = step_node( p, jn*32+int( lane ), a.S ) ;
+#pragma unroll
+							for ( int jj = 0 ; jj<RTX_K ; jj++ ) if ( jj == jn ) kinds[jj] = kn ;
+						}
+						jn = -1 ;
+#pragma unroll
+						for ( int jj = RTX_K-1 ; jj>=0 ; jj-- ) if ( kinds[jj] == K_NODE ) jn = jj ;
+						if ( __popc( __ballot_sync( 0xffffffffu, jn>=0 ) )<RTX_STICKY )
+							break ;
+					}
+					j = -1 ;   // kinds[] already updated
 					break ;
+				}
 				case K_LEAF:
 					if ( j>=0 ) nk = step_leaf( p, slot, a.S ) ;
 					break ;

@@ -27,9 +27,12 @@
 namespace rtx {
 
 #ifndef RTX_K
-#define RTX_K 3                 // ray slots per lane
+#define RTX_K 1                 // ray slots per lane (1: state in registers; >1: in shared memory)
 #endif
-#define RTX_POOL_STACK 16       // stack entries per slot kept in shared memory
+#if RTX_K == 1 && ! defined( RTX_REGPOOL )
+#define RTX_REGPOOL 1
+#endif
+#define RTX_POOL_STACK 16       // stack entries (work item + its entry distance) per slot kept in shared memory
 #define RTX_POOL_OVF   80       // further entries per slot in a global overflow area
 
 // slot fields (32-bit words)
@@ -42,7 +45,7 @@ enum {
 	F_NODES0, F_NODES1, F_TRIS0, F_TRIS1,                    // node / triangle arrays of the current level
 	F_THRX, F_THRY, F_THRZ, F_RNG0, F_RNG1, F_PIX, F_META,   // path: throughput, stream, tile pixel, sample<<8|depth left
 	F_STACK,
-	F_WORDS = F_STACK+RTX_POOL_STACK
+	F_WORDS = F_STACK+2*RTX_POOL_STACK
 } ;
 
 enum { K_DONE = 0, K_NODE = 1, K_LEAF = 2, K_THING = 3, K_SHADE = 4, K_REGEN = 5, K_KINDS = 6 } ;
@@ -56,15 +59,25 @@ struct DevPool {
 	__device__ __forceinline__ int32_t  i( int fld, int slot ) const { return int32_t( w[fld*( 32*RTX_K )+slot] ) ; }
 	__device__ __forceinline__ void     sf( int fld, int slot, float v ) { w[fld*( 32*RTX_K )+slot] = __float_as_uint( v ) ; }
 	__device__ __forceinline__ void     si( int fld, int slot, int32_t v ) { w[fld*( 32*RTX_K )+slot] = uint32_t( v ) ; }
-	__device__ __forceinline__ void     push( int slot, int32_t& sp, int32_t v ) {
-		if ( sp<RTX_POOL_STACK ) w[( F_STACK+sp )*( 32*RTX_K )+slot] = uint32_t( v ) ;
-		else if ( sp<RTX_POOL_STACK+RTX_POOL_OVF ) ovf[slot*RTX_POOL_OVF+( sp-RTX_POOL_STACK )] = v ;
+	__device__ __forceinline__ void     push( int slot, int32_t& sp, int32_t v, float t ) {
+		if ( sp<RTX_POOL_STACK ) {
+			w[( F_STACK+2*sp )*( 32*RTX_K )+slot] = uint32_t( v ) ;
+			w[( F_STACK+2*sp+1 )*( 32*RTX_K )+slot] = __float_as_uint( t ) ;
+		} else if ( sp<RTX_POOL_STACK+RTX_POOL_OVF ) {
+			ovf[( slot*RTX_POOL_OVF+( sp-RTX_POOL_STACK ) )*2] = v ;
+			ovf[( slot*RTX_POOL_OVF+( sp-RTX_POOL_STACK ) )*2+1] = __float_as_int( t ) ;
+		}
 		sp++ ;
 	}
-	__device__ __forceinline__ int32_t  pop( int slot, int32_t& sp ) {
+	__device__ __forceinline__ int32_t  pop( int slot, int32_t& sp, float& t ) {
 		sp-- ;
-		if ( sp<RTX_POOL_STACK ) return int32_t( w[( F_STACK+sp )*( 32*RTX_K )+slot] ) ;
-		return sp<RTX_POOL_STACK+RTX_POOL_OVF ? ovf[slot*RTX_POOL_OVF+( sp-RTX_POOL_STACK )] : RTX_STK_DONE ;
+		if ( sp<RTX_POOL_STACK ) {
+			t = __uint_as_float( w[( F_STACK+2*sp+1 )*( 32*RTX_K )+slot] ) ;
+			return int32_t( w[( F_STACK+2*sp )*( 32*RTX_K )+slot] ) ;
+		}
+		if ( sp>=RTX_POOL_STACK+RTX_POOL_OVF ) { t = 0.f ; return RTX_STK_DONE ; }
+		t = __int_as_float( ovf[( slot*RTX_POOL_OVF+( sp-RTX_POOL_STACK ) )*2+1] ) ;
+		return ovf[( slot*RTX_POOL_OVF+( sp-RTX_POOL_STACK ) )*2] ;
 	}
 } ;
 #endif
@@ -76,20 +89,22 @@ struct DevPool {
 struct RegPool {
 	uint32_t  r[F_STACK] ;
 	uint32_t* stk ;    // this lane's stack column in shared memory, stride 32
-	int32_t*  ovf ;
+	int32_t*  ovf ;    // this lane's overflow entries (pairs)
 	__device__ __forceinline__ float    f( int fld, int ) const { return __uint_as_float( r[fld] ) ; }
 	__device__ __forceinline__ int32_t  i( int fld, int ) const { return int32_t( r[fld] ) ; }
 	__device__ __forceinline__ void     sf( int fld, int, float v ) { r[fld] = __float_as_uint( v ) ; }
 	__device__ __forceinline__ void     si( int fld, int, int32_t v ) { r[fld] = uint32_t( v ) ; }
-	__device__ __forceinline__ void     push( int, int32_t& sp, int32_t v ) {
-		if ( sp<RTX_POOL_STACK ) stk[sp*32] = uint32_t( v ) ;
-		else if ( sp<RTX_POOL_STACK+RTX_POOL_OVF ) ovf[sp-RTX_POOL_STACK] = v ;
+	__device__ __forceinline__ void     push( int, int32_t& sp, int32_t v, float t ) {
+		if ( sp<RTX_POOL_STACK ) { stk[2*sp*32] = uint32_t( v ) ; stk[( 2*sp+1 )*32] = __float_as_uint( t ) ; }
+		else if ( sp<RTX_POOL_STACK+RTX_POOL_OVF ) { ovf[2*( sp-RTX_POOL_STACK )] = v ; ovf[2*( sp-RTX_POOL_STACK )+1] = __float_as_int( t ) ; }
 		sp++ ;
 	}
-	__device__ __forceinline__ int32_t  pop( int, int32_t& sp ) {
+	__device__ __forceinline__ int32_t  pop( int, int32_t& sp, float& t ) {
 		sp-- ;
-		if ( sp<RTX_POOL_STACK ) return int32_t( stk[sp*32] ) ;
-		return sp<RTX_POOL_STACK+RTX_POOL_OVF ? ovf[sp-RTX_POOL_STACK] : RTX_STK_DONE ;
+		if ( sp<RTX_POOL_STACK ) { t = __uint_as_float( stk[( 2*sp+1 )*32] ) ; return int32_t( stk[2*sp*32] ) ; }
+		if ( sp>=RTX_POOL_STACK+RTX_POOL_OVF ) { t = 0.f ; return RTX_STK_DONE ; }
+		t = __int_as_float( ovf[2*( sp-RTX_POOL_STACK )+1] ) ;
+		return ovf[2*( sp-RTX_POOL_STACK )] ;
 	}
 } ;
 #endif
@@ -129,25 +144,32 @@ template <class P> RTX_HD void begin_ray( P& p, int slot, const SceneDev& S, con
 	p.si( F_LEVEL, slot, -1 ) ;
 	stp( p, F_NODES0, slot, S.tlas_nodes ) ; stp( p, F_TRIS0, slot, nullptr ) ;
 	int32_t sp = 0 ;
-	p.push( slot, sp, RTX_STK_DONE ) ;
+	p.push( slot, sp, RTX_STK_DONE, 0.f ) ;
 	p.si( F_SP, slot, sp ) ;
 	p.si( F_CUR, slot, S.n_things ? 0 : RTX_STK_DONE ) ;   // 0 = root of the top level
 	if ( S.n_things ) prefetch_line( S.tlas_nodes ) ;
 }
 
-// pop the next work item; leaving a mesh (RTX_STK_RETURN) is handled on the way
+// pop the next work item.  Entries whose box the ray enters beyond the best hit found since
+// they were pushed are dropped without touching their node; leaving a mesh (RTX_STK_RETURN)
+// is handled on the way.
 template <class P> RTX_HD int32_t pop_next( P& p, int slot, const SceneDev& S, int32_t& sp, int32_t& level ) {
-	int32_t cur = p.pop( slot, sp ) ;
-	if ( cur == RTX_STK_RETURN ) {
-		const f3 o = ld3( p, F_OX, slot ), d = ld3( p, F_DX, slot ) ;
-		const f3 idir = mk3( safe_rcp( d.x ), safe_rcp( d.y ), safe_rcp( d.z ) ) ;
-		st3( p, F_IX, slot, idir ) ; st3( p, F_QX, slot, mk3( o.x*idir.x, o.y*idir.y, o.z*idir.z ) ) ;
-		level = -1 ;
-		p.si( F_LEVEL, slot, -1 ) ;
-		stp( p, F_NODES0, slot, S.tlas_nodes ) ; stp( p, F_TRIS0, slot, nullptr ) ;
-		cur = p.pop( slot, sp ) ;
+	const float tbest_s = p.f( F_T, slot )*RTX_SLACK ;
+	while ( true ) {
+		float t ;
+		const int32_t cur = p.pop( slot, sp, t ) ;
+		if ( cur == RTX_STK_RETURN ) {
+			const f3 o = ld3( p, F_OX, slot ), d = ld3( p, F_DX, slot ) ;
+			const f3 idir = mk3( safe_rcp( d.x ), safe_rcp( d.y ), safe_rcp( d.z ) ) ;
+			st3( p, F_IX, slot, idir ) ; st3( p, F_QX, slot, mk3( o.x*idir.x, o.y*idir.y, o.z*idir.z ) ) ;
+			level = -1 ;
+			p.si( F_LEVEL, slot, -1 ) ;
+			stp( p, F_NODES0, slot, S.tlas_nodes ) ; stp( p, F_TRIS0, slot, nullptr ) ;
+			continue ;
+		}
+		if ( cur == RTX_STK_DONE || t<=tbest_s )
+			return cur ;
 	}
-	return cur ;
 }
 
 // store the next work item and prefetch what it will read
@@ -168,6 +190,7 @@ template <class P> RTX_HD int step_node( P& p, int slot, const SceneDev& S ) {
 	const float tbest_s = p.f( F_T, slot )*RTX_SLACK ;
 	const float tmin = 1e-3f ;
 	const q4* n = ldp<P, q4>( p, F_NODES0, slot )+size_t( cur )*RTX_NODE_RECS ;
+	RTX_COUNT( nodes ) ;
 	const q4 lx = ldq( n ), ly = ldq( n+1 ), lz = ldq( n+2 ), hx = ldq( n+3 ), hy = ldq( n+4 ), hz = ldq( n+5 ), rf = ldq( n+6 ) ;
 	int32_t c0 = asint( rf.x ), c1 = asint( rf.y ), c2 = asint( rf.z ), c3 = asint( rf.w ) ;
 	float t0 = slab( lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, idir, ood, tmin, tbest_s ) ;
@@ -184,9 +207,9 @@ template <class P> RTX_HD int step_node( P& p, int slot, const SceneDev& S ) {
 	if ( t0 == INFINITY )
 		cur = pop_next( p, slot, S, sp, level ) ;
 	else {
-		if ( t3<INFINITY ) p.push( slot, sp, c3 ) ;
-		if ( t2<INFINITY ) p.push( slot, sp, c2 ) ;
-		if ( t1<INFINITY ) p.push( slot, sp, c1 ) ;
+		if ( t3<INFINITY ) p.push( slot, sp, c3, t3 ) ;
+		if ( t2<INFINITY ) p.push( slot, sp, c2, t2 ) ;
+		if ( t1<INFINITY ) p.push( slot, sp, c1, t1 ) ;
 		cur = c0 ;
 	}
 	return finish_step( p, slot, cur, sp, level ) ;
@@ -202,7 +225,9 @@ template <class P> RTX_HD int step_leaf( P& p, int slot, const SceneDev& S ) {
 	best.t = p.f( F_T, slot ) ; best.thing = p.i( F_THING, slot ) ; best.prim = p.i( F_PRIM, slot ) ; best.u = 0.f ; best.v = 0.f ;
 	const q4* tris = ldp<P, q4>( p, F_TRIS0, slot ) ;
 	bool changed = false ;
+	RTX_COUNT( leaves ) ;
 	for ( uint32_t k = 0 ; k<count ; k++ ) {
+		RTX_COUNT( tris ) ;
 		const q4* T = tris+size_t( first+k )*3 ;
 		const q4 a = ldq( T ), b = ldq( T+1 ), c = ldq( T+2 ) ;
 		float t, u, v ;
@@ -228,6 +253,7 @@ template <class P> RTX_HD int step_thing( P& p, int slot, const SceneDev& S ) {
 	const uint32_t first = uint32_t( ~cur )>>3 ;
 	const int32_t k = int32_t( RTX_LDG( S.tlas_order+first ) ) ;
 	const ThingTrav* tt = S.trav+k ;
+	RTX_COUNT( things ) ;
 	const f3 o = ld3( p, F_OX, slot ), d = ld3( p, F_DX, slot ) ;
 	const double m0 = RTX_LDG( tt->inv+0 ), m1 = RTX_LDG( tt->inv+1 ), m2 = RTX_LDG( tt->inv+2 ), m3 = RTX_LDG( tt->inv+3 ) ;
 	if ( RTX_LDG( &tt->kind ) == 0 ) {
@@ -256,7 +282,7 @@ template <class P> RTX_HD int step_thing( P& p, int slot, const SceneDev& S ) {
 	st3( p, F_IX, slot, idir ) ; st3( p, F_QX, slot, mk3( ohi.x*idir.x, ohi.y*idir.y, ohi.z*idir.z ) ) ;
 	stp( p, F_NODES0, slot, ldptr( &tt->nodes ) ) ; stp( p, F_TRIS0, slot, ldptr( &tt->tris ) ) ;
 	p.si( F_LEVEL, slot, k ) ;
-	p.push( slot, sp, RTX_STK_RETURN ) ;
+	p.push( slot, sp, RTX_STK_RETURN, 0.f ) ;
 	return finish_step( p, slot, 0, sp, k ) ;
 }
 
@@ -264,6 +290,7 @@ template <class P> RTX_HD int step_thing( P& p, int slot, const SceneDev& S ) {
 // or K_REGEN (path ended; `c` is its colour).  rtow.cxx:34-49.
 template <class P> RTX_HD int step_shade( P& p, int slot, const SceneDev& S, f3& c ) {
 	HitRec h ;
+	RTX_COUNT( rays ) ;
 	h.t = p.f( F_T, slot ) ; h.thing = p.i( F_THING, slot ) ; h.prim = p.i( F_PRIM, slot ) ; h.u = p.f( F_U, slot ) ; h.v = p.f( F_V, slot ) ;
 	const f3 ori = ld3( p, F_OX, slot ), dir = ld3( p, F_DX, slot ) ;
 	f3 thr = ld3( p, F_THRX, slot ) ;

@@ -75,3 +75,4 @@ def trace(things, cam, w, h, spp, depth=50, seed=4711, meshes=None):
     if got > cap:
         raise RuntimeError("trace larger than the buffer")
     return buf.raw[:got]
+

@@ -35,13 +35,25 @@ struct HostStack {
 
 // one ray slot, array backed: the store the step functions of rtx_pool.cuh run on here
 struct HostPool {
-	uint32_t w[F_WORDS] ; int32_t ovf[256] ;
+	uint32_t w[F_WORDS] ; int32_t ovf[512] ;
 	RTX_HD float   f( int fld, int ) const { float v ; memcpy( &v, &w[fld], 4 ) ; return v ; }
 	RTX_HD int32_t i( int fld, int ) const { return int32_t( w[fld] ) ; }
 	RTX_HD void    sf( int fld, int, float v ) { memcpy( &w[fld], &v, 4 ) ; }
 	RTX_HD void    si( int fld, int, int32_t v ) { w[fld] = uint32_t( v ) ; }
-	RTX_HD void    push( int, int32_t& sp, int32_t v ) { if ( sp<RTX_POOL_STACK ) w[F_STACK+sp] = uint32_t( v ) ; else ovf[sp-RTX_POOL_STACK] = v ; sp++ ; }
-	RTX_HD int32_t pop( int, int32_t& sp ) { sp-- ; return sp<RTX_POOL_STACK ? int32_t( w[F_STACK+sp] ) : ovf[sp-RTX_POOL_STACK] ; }
+	RTX_HD void    push( int, int32_t& sp, int32_t v, float t ) {
+		uint32_t tb ; memcpy( &tb, &t, 4 ) ;
+		if ( sp<RTX_POOL_STACK ) { w[F_STACK+2*sp] = uint32_t( v ) ; w[F_STACK+2*sp+1] = tb ; }
+		else { ovf[2*( sp-RTX_POOL_STACK )] = v ; ovf[2*( sp-RTX_POOL_STACK )+1] = int32_t( tb ) ; }
+		sp++ ;
+	}
+	RTX_HD int32_t pop( int, int32_t& sp, float& t ) {
+		sp-- ;
+		uint32_t tb ; int32_t v ;
+		if ( sp<RTX_POOL_STACK ) { v = int32_t( w[F_STACK+2*sp] ) ; tb = w[F_STACK+2*sp+1] ; }
+		else { v = ovf[2*( sp-RTX_POOL_STACK )] ; tb = uint32_t( ovf[2*( sp-RTX_POOL_STACK )+1] ) ; }
+		memcpy( &t, &tb, 4 ) ;
+		return v ;
+	}
 } ;
 
 // a whole path through the state machine of the render kernel
