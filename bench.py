@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--mode", default="mesh", choices=["mesh", "analytic"])
     ap.add_argument("--ndiv", type=int, default=None, help="one subdivision count for every sphere (default: reference mix)")
     ap.add_argument("--seed", type=int, default=4711)
+    ap.add_argument("--scene", default="book1", help="book1 (default) or grid<N>: N x N field of small spheres (stress scene, BASELINE configs[4])")
     ap.add_argument("--cpu-spp", type=int, default=2, help="samples per pixel of the CPU baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     return ap.parse_args()
@@ -59,7 +60,17 @@ def parse():
 
 def workload_name(a):
     geo = "analytic spheres" if a.mode == "analytic" else ("tessellated ndiv %d" % a.ndiv if a.ndiv is not None else "tessellated 9/6/3/8/6/3")
-    return "RTOW book-1 random spheres, %s, %dx%d, %d spp, depth %d, defocus on" % (geo, a.width, a.height, a.spp, a.depth)
+    name = "RTOW book-1 random spheres" if a.scene == "book1" else "%s field of spheres" % a.scene
+    return "%s, %s, %dx%d, %d spp, depth %d, defocus on" % (name, geo, a.width, a.height, a.spp, a.depth)
+
+
+def make_scene(a):
+    from rtxplay_b200 import scenes
+    if a.scene == "book1":
+        return scenes.book1(seed=1)
+    if a.scene.startswith("grid"):
+        return scenes.grid_field(int(a.scene[4:]), seed=2, ndiv=6 if a.ndiv is None else a.ndiv)
+    raise SystemExit("unknown --scene " + a.scene)
 
 
 # ------------------------------------------------------------------------- CPU legs
@@ -68,7 +79,7 @@ def cpu_leg(a, spp, steps=1, warmup=0):
     scan) on `spp` samples per pixel of the same image; returns (segments/s, cores, description)."""
     import oracle as orc
     from rtxplay_b200 import scenes
-    spheres = scenes.book1(seed=1)
+    spheres = make_scene(a)
     tab, _ = scenes.table(spheres, "analytic")
     cam = orc.camera_f32((13, 2, 3), (0, 0, 0), (0, 1, 0), 20., a.width / a.height, .1, 10.)
     cores = os.cpu_count() or 1
@@ -154,8 +165,8 @@ def run_b200(a):
 
     # scene + acceleration structures (outside the timed window, like optx/rtwo.cxx:133-250)
     ctx = api.Context(local)
-    spheres = scenes.book1(seed=1)
-    scenes.load(ctx, spheres, a.mode, a.ndiv)
+    spheres = make_scene(a)
+    scenes.load(ctx, spheres, a.mode, a.ndiv if a.scene == "book1" else None)
     ctx.resize(a.width, a.height)
     cam = api.camera(aspratio=a.width / a.height)
     st0 = ctx.stats()
@@ -252,6 +263,7 @@ def run_b200(a):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(a), "segments_per_frame": segments, "paths_per_frame": a.width * a.height * a.spp,
+                       "build_ms": {"meshes": st["ms_build_blas"], "top_level": st["ms_build_tlas"]}, "device_mb": st["bytes_device"] / 1048576.,
                        "things": st["n_things"], "triangles_instanced": st["n_triangles_instanced"], "triangles_stored": st["n_triangles"],
                        "parallelism": "spp split over %d rank(s) + NCCL reduce of the u64 accumulation buffer" % world if world > 1 else "1 GPU",
                        "l2": "256 MiB device write between steps (inside the timed region)",

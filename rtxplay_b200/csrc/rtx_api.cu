@@ -426,7 +426,7 @@ void rtx_shutdown( rtx_ctx* c ) {
 	cudaSetDevice( c->device ) ;
 	cudaStreamSynchronize( c->stream ) ;
 	for ( Mesh& m : c->meshes ) {
-		dfree( c, m.vces, 3*size_t( m.nv ) ) ; dfree( c, m.ices, 3*size_t( m.nt ) ) ; dfree( c, m.tris, 3*size_t( m.nt ) ) ;
+		dfree( c, m.vces, 3*size_t( m.nv ) ) ; dfree( c, m.ices, 3*size_t( m.nt ) ) ; dfree( c, m.tris, RTX_TRI_RECS*size_t( m.nt ) ) ;
 		lbvh_free( c, m.bvh ) ;
 	}
 	lbvh_free( c, c->tlas ) ;
@@ -452,7 +452,7 @@ int rtx_mesh_create( rtx_ctx* c, const float* xyz, uint32_t nv, const uint32_t* 
 		if ( idx[k]>=nv ) throw std::runtime_error( "rtx_mesh_create: index out of bounds" ) ;   // optx/object.cxx:62-67
 	Mesh m ;
 	m.nv = nv ; m.nt = nt ;
-	m.vces = dalloc<float>( c, 3*size_t( nv ) ) ; m.ices = dalloc<uint32_t>( c, 3*size_t( nt ) ) ; m.tris = dalloc<q4>( c, 3*size_t( nt ) ) ;
+	m.vces = dalloc<float>( c, 3*size_t( nv ) ) ; m.ices = dalloc<uint32_t>( c, 3*size_t( nt ) ) ; m.tris = dalloc<q4>( c, RTX_TRI_RECS*size_t( nt ) ) ;
 	CK( cudaMemcpyAsync( m.vces, xyz, sizeof( float )*3*nv, cudaMemcpyHostToDevice, c->stream ) ) ;
 	CK( cudaMemcpyAsync( m.ices, idx, sizeof( uint32_t )*3*size_t( nt ), cudaMemcpyHostToDevice, c->stream ) ) ;
 	q4* plo = dalloc<q4>( c, nt ) ; q4* phi = dalloc<q4>( c, nt ) ;

@@ -130,6 +130,7 @@ struct q4 { float x, y, z, w ; } ;   // 16-byte record, bit-compatible with floa
 // (count-1); RTX_REF_EMPTY marks an unused slot.  The two values above it are stack
 // sentinels.
 #define RTX_NODE_RECS  8
+#define RTX_TRI_RECS   4            // a triangle: (v0, prim id) (e1,-) (e2,-) (pad) = 64 bytes, two 256-bit loads
 #define RTX_WIDTH      4
 #define RTX_LEAF_MAX   4            // triangles per mesh leaf (top level: 1 thing per leaf)
 #define RTX_REF_EMPTY  0x7ffffffd
@@ -140,7 +141,7 @@ struct q4 { float x, y, z, w ; } ;   // 16-byte record, bit-compatible with floa
 struct ThingTrav {
 	double     inv[12] ;   // world->object (mesh); analytic sphere: inv[0..3] = cx, cy, cz, r
 	const q4*  nodes ;     // mesh LBVH
-	const q4*  tris ;      // mesh triangles in leaf order: (v0, asfloat(prim)), (e1,-), (e2,-)
+	const q4*  tris ;      // mesh triangles in leaf order: (v0, asfloat(prim)), (e1,-), (e2,-), pad
 	int32_t    kind ;      // 0 analytic sphere, 1 mesh instance
 	uint32_t   n_tris ;
 	int32_t    pad[2] ;
@@ -185,6 +186,20 @@ RTX_HD q4 ldq( const q4* p ) {
 #else
 	return *p ;
 #endif
+}
+// two adjacent records with ONE 256-bit load (sm_100: LDG.E.256): a lane that fetches a
+// whole 128-byte node touches its cache line 4 times instead of 7 -- the L1 tag stage was a
+// co-bottleneck of the traversal (ncu: l1tex throughput 47 %)
+struct o8 { q4 a, b ; } ;
+RTX_HD o8 ldo( const q4* p ) {
+	o8 r ;
+#if defined( __CUDA_ARCH__ )
+	asm( "ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		: "=f"( r.a.x ), "=f"( r.a.y ), "=f"( r.a.z ), "=f"( r.a.w ), "=f"( r.b.x ), "=f"( r.b.y ), "=f"( r.b.z ), "=f"( r.b.w ) : "l"( p ) ) ;
+#else
+	r.a = p[0] ; r.b = p[1] ;
+#endif
+	return r ;
 }
 // __ldg has no pointer overload: read the 8 bytes as an integer
 template <class T> RTX_HD const T* ldptr( const T* const* pp ) {
@@ -314,7 +329,8 @@ RTX_HD void closest( const SceneDev& S, const f3& o, const f3& d, float tmin, St
 			if ( uint32_t( cur )<uint32_t( RTX_REF_EMPTY ) ) {
 				const q4* n = nodes+size_t( cur )*RTX_NODE_RECS ;
 				RTX_COUNT( nodes ) ; RTX_EVENT( 'N' ) ;
-				const q4 lx = ldq( n ), ly = ldq( n+1 ), lz = ldq( n+2 ), hx = ldq( n+3 ), hy = ldq( n+4 ), hz = ldq( n+5 ), rf = ldq( n+6 ) ;
+				const o8 n01 = ldo( n ), n23 = ldo( n+2 ), n45 = ldo( n+4 ), n67 = ldo( n+6 ) ;
+				const q4 lx = n01.a, ly = n01.b, lz = n23.a, hx = n23.b, hy = n45.a, hz = n45.b, rf = n67.a ;
 				int32_t c0 = asint( rf.x ), c1 = asint( rf.y ), c2 = asint( rf.z ), c3 = asint( rf.w ) ;
 				float t0 = slab( lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, idir, ood, tmin, tbest_s ) ;
 				float t1 = slab( lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, idir, ood, tmin, tbest_s ) ;
@@ -355,8 +371,9 @@ RTX_HD void closest( const SceneDev& S, const f3& o, const f3& d, float tmin, St
 				RTX_COUNT( leaves ) ; RTX_EVENT( char( '0'+count ) ) ;
 				for ( uint32_t k = 0 ; k<count ; k++ ) {
 					RTX_COUNT( tris ) ;
-					const q4* T = tris+size_t( first+k )*3 ;
-					const q4 a = ldq( T ), b = ldq( T+1 ), c = ldq( T+2 ) ;
+					const q4* T = tris+size_t( first+k )*RTX_TRI_RECS ;
+					const o8 t01 = ldo( T ), t23 = ldo( T+2 ) ;
+					const q4 a = t01.a, b = t01.b, c = t23.a ;
 					float t, u, v ;
 					if ( tri_test( mk3( a.x, a.y, a.z ), mk3( b.x, b.y, b.z ), mk3( c.x, c.y, c.z ), ohi, olo, dd, tmin, t, u, v ) ) {
 						const int32_t prim = asint( a.w ) ;
@@ -424,7 +441,7 @@ RTX_HD void closest_brute( const SceneDev& S, const f3& o, const f3& d, float tm
 			const f3 olo = narrow( od-wide( ohi ) ) ;
 			const f3 dd  = narrow( xfvec( tt->inv, wide( d ) ) ) ;
 			for ( uint32_t f = 0 ; f<tt->n_tris ; f++ ) {
-				const q4* T = tt->tris+size_t( f )*3 ;
+				const q4* T = tt->tris+size_t( f )*RTX_TRI_RECS ;
 				const q4 a = ldq( T ), b = ldq( T+1 ), c = ldq( T+2 ) ;
 				float t, u, v ;
 				if ( tri_test( mk3( a.x, a.y, a.z ), mk3( b.x, b.y, b.z ), mk3( c.x, c.y, c.z ), ohi, olo, dd, tmin, t, u, v ) ) {

@@ -310,10 +310,11 @@ __global__ void __launch_bounds__( 256 ) k_pack_tris( const float* vces, const u
 	const uint32_t f = vals[j] ;
 	const uint32_t i0 = ices[3*size_t( f )], i1 = ices[3*size_t( f )+1], i2 = ices[3*size_t( f )+2] ;
 	const float* a = vces+3*size_t( i0 ) ; const float* b = vces+3*size_t( i1 ) ; const float* c = vces+3*size_t( i2 ) ;
-	q4* T = tris+size_t( j )*3 ;
+	q4* T = tris+size_t( j )*RTX_TRI_RECS ;
 	T[0] = { a[0], a[1], a[2], __int_as_float( int( f ) ) } ;
 	T[1] = { b[0]-a[0], b[1]-a[1], b[2]-a[2], 0.f } ;
 	T[2] = { c[0]-a[0], c[1]-a[1], c[2]-a[2], 0.f } ;
+	T[3] = { 0.f, 0.f, 0.f, 0.f } ;
 }
 // world bounds of every thing: analytic sphere c +- r; mesh = its root box corners mapped
 // through the double transform.  root boxes are [lo,hi] of each thing's mesh.

@@ -179,7 +179,7 @@ template <class P> RTX_HD int finish_step( P& p, int slot, int32_t cur, int32_t 
 	if ( kind == K_NODE )
 		prefetch_line( ldp<P, q4>( p, F_NODES0, slot )+size_t( cur )*RTX_NODE_RECS ) ;
 	else if ( kind == K_LEAF )
-		prefetch_line( ldp<P, q4>( p, F_TRIS0, slot )+size_t( uint32_t( ~cur )>>3 )*3 ) ;
+		prefetch_line( ldp<P, q4>( p, F_TRIS0, slot )+size_t( uint32_t( ~cur )>>3 )*RTX_TRI_RECS ) ;
 	return kind ;
 }
 
@@ -191,7 +191,8 @@ template <class P> RTX_HD int step_node( P& p, int slot, const SceneDev& S ) {
 	const float tmin = 1e-3f ;
 	const q4* n = ldp<P, q4>( p, F_NODES0, slot )+size_t( cur )*RTX_NODE_RECS ;
 	RTX_COUNT( nodes ) ;
-	const q4 lx = ldq( n ), ly = ldq( n+1 ), lz = ldq( n+2 ), hx = ldq( n+3 ), hy = ldq( n+4 ), hz = ldq( n+5 ), rf = ldq( n+6 ) ;
+	const o8 n01 = ldo( n ), n23 = ldo( n+2 ), n45 = ldo( n+4 ), n67 = ldo( n+6 ) ;
+	const q4 lx = n01.a, ly = n01.b, lz = n23.a, hx = n23.b, hy = n45.a, hz = n45.b, rf = n67.a ;
 	int32_t c0 = asint( rf.x ), c1 = asint( rf.y ), c2 = asint( rf.z ), c3 = asint( rf.w ) ;
 	float t0 = slab( lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, idir, ood, tmin, tbest_s ) ;
 	float t1 = slab( lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, idir, ood, tmin, tbest_s ) ;
@@ -228,8 +229,9 @@ template <class P> RTX_HD int step_leaf( P& p, int slot, const SceneDev& S ) {
 	RTX_COUNT( leaves ) ;
 	for ( uint32_t k = 0 ; k<count ; k++ ) {
 		RTX_COUNT( tris ) ;
-		const q4* T = tris+size_t( first+k )*3 ;
-		const q4 a = ldq( T ), b = ldq( T+1 ), c = ldq( T+2 ) ;
+		const q4* T = tris+size_t( first+k )*RTX_TRI_RECS ;
+		const o8 t01 = ldo( T ), t23 = ldo( T+2 ) ;
+		const q4 a = t01.a, b = t01.b, c = t23.a ;
 		float t, u, v ;
 		if ( tri_test( mk3( a.x, a.y, a.z ), mk3( b.x, b.y, b.z ), mk3( c.x, c.y, c.z ), ohi, olo, dd, 1e-3f, t, u, v ) ) {
 			const int32_t prim = asint( a.w ) ;

@@ -194,13 +194,13 @@ void build_scene( EmuScene& E, const double* things, int n_things, int n_meshes,
 			phi[f] = { fmaxf( a[0], fmaxf( b[0], c[0] ) ), fmaxf( a[1], fmaxf( b[1], c[1] ) ), fmaxf( a[2], fmaxf( b[2], c[2] ) ), 0.f } ;
 		}
 		build_tree( plo, phi, m.tree, RTX_LEAF_MAX ) ;
-		m.tris.resize( 3*size_t( nt[q] ) ) ;
+		m.tris.assign( RTX_TRI_RECS*size_t( nt[q] ), q4{ 0, 0, 0, 0 } ) ;
 		for ( uint32_t j = 0 ; j<nt[q] ; j++ ) {
 			const uint32_t f = m.tree.order[j] ;
 			const float* a = &m.vces[3*size_t( m.ices[3*f] )] ; const float* b = &m.vces[3*size_t( m.ices[3*f+1] )] ; const float* c = &m.vces[3*size_t( m.ices[3*f+2] )] ;
-			m.tris[3*size_t( j )]   = { a[0], a[1], a[2], asfloat( int( f ) ) } ;
-			m.tris[3*size_t( j )+1] = { b[0]-a[0], b[1]-a[1], b[2]-a[2], 0.f } ;
-			m.tris[3*size_t( j )+2] = { c[0]-a[0], c[1]-a[1], c[2]-a[2], 0.f } ;
+			m.tris[RTX_TRI_RECS*size_t( j )]   = { a[0], a[1], a[2], asfloat( int( f ) ) } ;
+			m.tris[RTX_TRI_RECS*size_t( j )+1] = { b[0]-a[0], b[1]-a[1], b[2]-a[2], 0.f } ;
+			m.tris[RTX_TRI_RECS*size_t( j )+2] = { c[0]-a[0], c[1]-a[1], c[2]-a[2], 0.f } ;
 		}
 	}
 	E.trav.resize( n_things ) ; E.shade.resize( n_things ) ;
