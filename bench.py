@@ -255,6 +255,12 @@ def run_b200(a):
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         achieved = segs_launch * bytes_seg / (k_ms * 1e-3) / 1e9
+        # DRAM bytes of the kernel from the committed ncu capture of this same configuration
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "r01_k_render_traffic.json")
+        if os.path.exists(tpath) and world == 1 and a.scene == "book1" and a.mode == "mesh" and a.ndiv is None and (a.width, a.height, a.spp) == (1200, 800, 500):
+            t = json.load(open(tpath))
+            traffic, traffic_src = t["dram_bytes_read"] + t["dram_bytes_write"], "profiles/r01_k_render_traffic.json (" + t["source"] + ")"
         clocks = sampler.summary() if sampler else {}
         sm_mhz = clocks.get("sm_mhz") or 1965
         fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
@@ -269,9 +275,9 @@ def run_b200(a):
                        "l2": "256 MiB device write between steps (inside the timed region)",
                        "ms_per_frame": ms_step, "ms_per_frame_e2e": e2e_ms, "wall_ms_per_step": ms_wall / a.steps},
             "roofline": {"bound": "hbm", "kernel": "k_render", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "bytes_per_segment": bytes_seg, "kernel_ms": k_ms,
-                         "note": "algorithmic node+primitive bytes of SURVEY.md 8(d); the working set is L1/L2 resident, so this is a cache-bandwidth figure quoted against HBM peak",
+                         "note": "algorithmic node+primitive bytes of SURVEY.md 8(d); the working set is L1/L2 resident (ncu: 88 MB of DRAM traffic per launch against 2.2 TB of algorithmic bytes), so this is a cache-bandwidth figure quoted against the HBM peak; the kernel is bound by instruction issue and SIMD efficiency (DESIGN.md 4)",
                          "fp32": {"flop_per_segment": flop_seg, "achieved_tflops": segs_launch * flop_seg / (k_ms * 1e-3) / 1e12,
                                   "peak_tflops": fp32_peak, "frac": segs_launch * flop_seg / (k_ms * 1e-3) / 1e12 / fp32_peak}},
             "e2e": {"value": segments / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": ctypes.sizeof(ctx.params(cam, 1)),

@@ -50,6 +50,8 @@ typedef struct {
 	uint32_t   sample0 ;        /* global index of this call's first sample ... */
 	uint32_t   sample_stride ;  /* ... and the step between its samples (multi-GPU spp split) */
 	uint32_t   accumulate ;     /* 0: start from zero (optx/camera_i.cu:52); 1: add to the buffers */
+	uint32_t   guides ;         /* 1: also fill the denoiser guide layers normals / albedos (optx/camera_i.cu:56-57,
+	                               99-101, 109-113; optx/optics_i.cu:97-101, 185-189) */
 } rtx_params ;
 
 typedef struct {
@@ -75,7 +77,8 @@ enum {
 	RTX_BUF_HIT_T   = 5,  /* float[w*h]    its ray parameter */
 	RTX_BUF_NORMALS = 6,  /* float[3*w*h]  LpGeneral.normals (optx/launcher.cxx:43) */
 	RTX_BUF_ALBEDOS = 7,  /* float[3*w*h]  LpGeneral.albedos (optx/launcher.cxx:44) */
-	RTX_BUF_PICK_ID = 8   /* uint32[1]     LpGeneral.pick_id (optx/launcher.cxx:46), written by rtx_pick */
+	RTX_BUF_PICK_ID = 8,  /* uint32[1]     LpGeneral.pick_id (optx/launcher.cxx:46), written by rtx_pick */
+	RTX_BUF_GUIDE_ACC = 9 /* int64[6*w*h]  fixed-point (2^-30) sums of the guide layers: normal xyz, albedo rgb */
 } ;
 
 enum { RTX_PP_NONE = 0, RTX_PP_SRGB = 1 } ;

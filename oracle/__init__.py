@@ -87,7 +87,7 @@ class _Meshes:
 
 
 def render(kind, things, cam, w, h, spp, depth=50, seed=4711, sample0=0, sample_stride=1,
-           y0=0, y1=None, threads=0, meshes=None, want_first=False):
+           y0=0, y1=None, threads=0, meshes=None, want_first=False, want_guides=False):
     """Returns dict(sum=double[h,w,3], fix=uint64[h,w,3], rpp=uint32[h,w], first_id, first_t)."""
     L = lib()
     y1 = h if y1 is None else y1
@@ -98,15 +98,16 @@ def render(kind, things, cam, w, h, spp, depth=50, seed=4711, sample0=0, sample_
                rpp=np.zeros((h, w), dtype=np.uint32))
     fid = np.full((h, w), -1, dtype=np.int64) if want_first else None
     ft = np.full((h, w), -1.0, dtype=np.float64) if want_first else None
+    gd = np.zeros((h, w, 6), dtype=np.int64) if want_guides else None
     rc = L.orc_render(ctypes.c_int(kind), _p(things), ctypes.c_int(len(things)),
                       ctypes.c_int(M.n), M.vp, _p(M.nv), M.ip, _p(M.nt),
                       _p(cam), ctypes.c_int(w), ctypes.c_int(h), ctypes.c_int(spp), ctypes.c_int(depth),
                       ctypes.c_uint64(seed), ctypes.c_int(sample0), ctypes.c_int(sample_stride),
                       ctypes.c_int(y0), ctypes.c_int(y1), ctypes.c_int(threads),
-                      _p(out["sum"]), _p(out["fix"]), _p(out["rpp"]), _p(fid), _p(ft))
+                      _p(out["sum"]), _p(out["fix"]), _p(out["rpp"]), _p(fid), _p(ft), _p(gd))
     if rc != 0:
         raise RuntimeError("orc_render failed: %d" % rc)
-    out["first_id"], out["first_t"] = fid, ft
+    out["first_id"], out["first_t"], out["guide"] = fid, ft, gd
     return out
 
 

@@ -441,7 +441,13 @@ template <class R, class Rng> struct Tracer {
 	// rtow.cxx:34-49.  The reference recurses and multiplies attenuations on the way
 	// back (a1*(a2*(...*sky))); back_to_front=true reproduces that product order, false
 	// is the float-mirror contract: throughput front to back, then times the sky.
+	// guide layers (optx/optics_i.cu:97-101, 185-189): normal and albedo of the first diffuse
+	// or reflecting hit of the path that is shaded
+	bool  guide_set_ ;
+	V3<R> guide_n_, guide_a_ ;
+
 	V3<R> path( V3<R> ori, V3<R> dir, int depth, bool back_to_front, unsigned& segments, int* first_thing, int* first_prim, R* first_t ) {
+		guide_set_ = false ;
 		std::vector<V3<R>>& att = att_ ;
 		att.clear() ;
 		V3<R> tail ;
@@ -463,7 +469,11 @@ template <class R, class Rng> struct Tracer {
 			}
 			if ( shot ) {
 				V3<R> attened, out ;
-				if ( depth>0 && scatter( scene->things[h.thing], dir, h, attened, out ) ) {
+				const bool go = depth>0 && scatter( scene->things[h.thing], dir, h, attened, out ) ;
+				if ( depth>0 && ! guide_set_ && scene->things[h.thing].type != 2 ) {
+					guide_set_ = true ; guide_n_ = h.normal ; guide_a_ = scene->things[h.thing].albedo ;
+				}
+				if ( go ) {
 					att.push_back( attened ) ;
 					ori = h.p ; dir = out ; depth-- ;
 					continue ;
@@ -510,6 +520,7 @@ struct RenderArgs {
 	uint32_t* rpp ;                  // [h*w] segments per pixel or nullptr
 	int64_t*  first_id ;             // [h*w] (thing<<32|prim+1) of sample0's primary ray, -1 miss
 	double*   first_t ;              // [h*w]
+	int64_t*  guide ;                // [h*w*6] fixed-point (2^-30) sums of guide normal xyz, albedo rgb, or nullptr
 } ;
 
 // rtow.cxx:105-117: the pixel loop (rows h-1..0 for the libc stream, which is order
@@ -523,6 +534,7 @@ template <class R, class Rng> void render_rows( const SceneT<R>& scene, const do
 			const size_t pix = size_t( a.w )*y+x ;
 			V3<R> color = mk<R>( R( 0 ), R( 0 ), R( 0 ) ) ;
 			uint64_t fx[3] = { 0, 0, 0 } ;
+			int64_t gd[6] = { 0, 0, 0, 0, 0, 0 } ;
 			unsigned segments = 0 ;
 			for ( int k = 0 ; k<a.spp ; ++k ) {
 				const uint32_t sample = uint32_t( a.sample0+k*a.sample_stride ) ;
@@ -540,7 +552,12 @@ template <class R, class Rng> void render_rows( const SceneT<R>& scene, const do
 				}
 				color = color+c ;
 				fx[0] += tofix( c.x ) ; fx[1] += tofix( c.y ) ; fx[2] += tofix( c.z ) ;
+				if ( tr.guide_set_ ) {
+					const R v[6] = { tr.guide_n_.x, tr.guide_n_.y, tr.guide_n_.z, tr.guide_a_.x, tr.guide_a_.y, tr.guide_a_.z } ;
+					for ( int q = 0 ; q<6 ; q++ ) gd[q] += int64_t( v[q]*R( 1073741824 ) ) ;
+				}
 			}
+			if ( a.guide ) for ( int q = 0 ; q<6 ; q++ ) a.guide[6*pix+q] = gd[q] ;
 			if ( a.sum ) { a.sum[3*pix] = double( color.x ) ; a.sum[3*pix+1] = double( color.y ) ; a.sum[3*pix+2] = double( color.z ) ; }
 			if ( a.fix ) { a.fix[3*pix] = fx[0] ; a.fix[3*pix+1] = fx[1] ; a.fix[3*pix+2] = fx[2] ; }
 			if ( a.rpp ) a.rpp[pix] = segments ;
@@ -673,13 +690,13 @@ int orc_render( int kind, const double* things, int n_things,
 		int n_meshes, const float* const* vces, const uint32_t* nv, const uint32_t* const* ices, const uint32_t* nt,
 		const double* cam, int w, int h, int spp, int depth, uint64_t seed, int sample0, int sample_stride,
 		int y0, int y1, int threads,
-		double* sum, uint64_t* fix, uint32_t* rpp, int64_t* first_id, double* first_t ) {
+		double* sum, uint64_t* fix, uint32_t* rpp, int64_t* first_id, double* first_t, int64_t* guide ) {
 	std::vector<MeshRef> m( n_meshes ) ;
 	for ( int q = 0 ; q<n_meshes ; q++ ) { m[q].vces = vces[q] ; m[q].nv = nv[q] ; m[q].ices = ices[q] ; m[q].nt = nt[q] ; }
 	RenderArgs a ;
 	a.w = w ; a.h = h ; a.spp = spp ; a.depth = depth ; a.seed = seed ; a.sample0 = sample0 ; a.sample_stride = sample_stride ;
 	a.y0 = y0 ; a.y1 = y1 ; a.threads = threads ;
-	a.sum = sum ; a.fix = fix ; a.rpp = rpp ; a.first_id = first_id ; a.first_t = first_t ;
+	a.sum = sum ; a.fix = fix ; a.rpp = rpp ; a.first_id = first_id ; a.first_t = first_t ; a.guide = guide ;
 	switch ( kind ) {
 		case ORC_F64_LIBC: a.back_to_front = 1 ; render<double, RngLibc>( things, n_things, m.data(), n_meshes, cam, a, false ) ; break ;
 		case ORC_F64_PCG:  a.back_to_front = 1 ; render<double, RngPcg>( things, n_things, m.data(), n_meshes, cam, a, true ) ; break ;

@@ -12,7 +12,7 @@ from . import _lib
 from ._lib import RtxCamera, RtxOptics, RtxParams, RtxStats
 
 DIFFUSE, REFLECT, REFRACT = 0, 1, 2
-BUF_ACCUM, BUF_RAWRGB, BUF_RPP, BUF_IMAGE, BUF_HIT_ID, BUF_HIT_T, BUF_NORMALS, BUF_ALBEDOS = range(8)
+BUF_ACCUM, BUF_RAWRGB, BUF_RPP, BUF_IMAGE, BUF_HIT_ID, BUF_HIT_T, BUF_NORMALS, BUF_ALBEDOS, BUF_PICK_ID, BUF_GUIDE_ACC = range(10)
 PP_NONE, PP_SRGB = 0, 1
 
 
@@ -128,11 +128,12 @@ class Context:
         self._ck(self._L.rtx_resize(self._c, ctypes.c_uint32(w), ctypes.c_uint32(h)))
         self.w, self.h = w, h
 
-    def params(self, cam, spp, depth=50, seed=4711, sample0=0, sample_stride=1, accumulate=0):
+    def params(self, cam, spp, depth=50, seed=4711, sample0=0, sample_stride=1, accumulate=0, guides=0):
         p = RtxParams()
         p.image_w, p.image_h, p.spp, p.depth = self.w, self.h, spp, depth
         p.camera = cam
         p.seed, p.sample0, p.sample_stride, p.accumulate = seed, sample0, sample_stride, accumulate
+        p.guides = guides
         return p
 
     def render(self, p):
@@ -169,7 +170,8 @@ class Context:
         return ids, ts
 
     _SHAPES = {BUF_ACCUM: (np.uint64, 4), BUF_RAWRGB: (np.float32, 3), BUF_RPP: (np.uint32, 0), BUF_IMAGE: (np.uint8, 4),
-               BUF_HIT_ID: (np.int64, 0), BUF_HIT_T: (np.float32, 0), BUF_NORMALS: (np.float32, 3), BUF_ALBEDOS: (np.float32, 3)}
+               BUF_HIT_ID: (np.int64, 0), BUF_HIT_T: (np.float32, 0), BUF_NORMALS: (np.float32, 3), BUF_ALBEDOS: (np.float32, 3),
+               BUF_GUIDE_ACC: (np.int64, 6)}
 
     def read(self, buffer):
         dt, ch = self._SHAPES[buffer]

@@ -102,6 +102,8 @@ struct rtx_ctx {
 	float*    d_hit_t = nullptr ;
 	float*    d_normals = nullptr ;
 	float*    d_albedos = nullptr ;
+	long long* d_guide_acc = nullptr ;   // allocated by the first frame that asks for guide layers
+	bool      guides_valid = false ;
 	uint32_t* d_pick = nullptr ;
 	unsigned long long* d_counter = nullptr ;
 	uint32_t* d_tile_counter = nullptr ;
@@ -298,6 +300,7 @@ void free_frame( rtx_ctx* c ) {
 	const size_t np = size_t( c->w )*c->h ;
 	dfree( c, c->d_accum, 4*np ) ; dfree( c, c->d_raw, 3*np ) ; dfree( c, c->d_rpp, np ) ; dfree( c, c->d_image, np ) ;
 	dfree( c, c->d_hit_id, np ) ; dfree( c, c->d_hit_t, np ) ; dfree( c, c->d_normals, 3*np ) ; dfree( c, c->d_albedos, 3*np ) ;
+	dfree( c, c->d_guide_acc, 6*np ) ; c->guides_valid = false ;
 }
 
 CameraDev camera_dev( const rtx_camera& k ) {
@@ -317,6 +320,12 @@ FrameArgs frame_args( rtx_ctx* c, const rtx_params* p ) {
 	a.w = p->image_w ; a.h = p->image_h ; a.spp = p->spp ; a.depth = p->depth ; a.seed = p->seed ;
 	a.sample0 = p->sample0 ; a.sample_stride = p->sample_stride ? p->sample_stride : 1u ; a.accumulate = p->accumulate ;
 	a.accum = c->d_accum ; a.hit_id = c->d_hit_id ; a.hit_t = c->d_hit_t ;
+	a.guides = p->guides ? 1u : 0u ;
+	if ( a.guides && ! c->d_guide_acc ) {
+		c->d_guide_acc = dalloc<long long>( c, 6*size_t( c->w )*c->h ) ;
+		CK( cudaMemsetAsync( c->d_guide_acc, 0, sizeof( long long )*6*size_t( c->w )*c->h, c->stream ) ) ;
+	}
+	a.guide_acc = c->d_guide_acc ;
 	return a ;
 }
 
@@ -324,16 +333,22 @@ void do_resolve( rtx_ctx* c, uint64_t total_spp ) {
 	const uint32_t np = c->w*c->h ;
 	k_resolve<<<( np+255 )/256, 256, 0, c->stream>>>( c->d_accum, np, total_spp ? total_spp : 1, c->d_raw, c->d_rpp ) ;
 	c->launches += 1 ;
+	if ( c->guides_valid ) {
+		k_resolve_guides<<<( np+255 )/256, 256, 0, c->stream>>>( c->d_guide_acc, np, total_spp ? total_spp : 1, c->d_normals, c->d_albedos ) ;
+		c->launches += 1 ;
+	}
 	CK( cudaGetLastError() ) ;
 }
 
 void do_render( rtx_ctx* c, const rtx_params* p, bool resolve ) {
 	const FrameArgs a = frame_args( c, p ) ;
+	c->guides_valid = a.guides != 0 ;
 	CK( cudaEventRecord( c->ev0, c->stream ) ) ;
 	if ( a.depth>255u ) throw std::runtime_error( "rtx: depth above 255 is not supported" ) ;
 	const uint32_t n_tiles = ( ( a.w+7u )>>3 )*( ( a.h+3u )>>2 ) ;
 	CK( cudaMemsetAsync( c->d_tile_counter, 0, sizeof( uint32_t ), c->stream ) ) ;
-	k_render<<<min( c->render_grid, n_tiles ), 32, 0, c->stream>>>( a, c->d_tile_counter, c->d_ovf ) ;
+	if ( a.guides ) k_render<true><<<min( c->render_grid, n_tiles ), 32, 0, c->stream>>>( a, c->d_tile_counter, c->d_ovf ) ;
+	else            k_render<false><<<min( c->render_grid, n_tiles ), 32, 0, c->stream>>>( a, c->d_tile_counter, c->d_ovf ) ;
 	c->launches += 1 ;
 	CK( cudaGetLastError() ) ;
 	CK( cudaEventRecord( c->ev1, c->stream ) ) ;
@@ -357,6 +372,7 @@ BufInfo buffer_of( rtx_ctx* c, int buffer ) {
 		case RTX_BUF_NORMALS: return { c->d_normals, np*3*sizeof( float ) } ;
 		case RTX_BUF_ALBEDOS: return { c->d_albedos, np*3*sizeof( float ) } ;
 		case RTX_BUF_PICK_ID: return { c->d_pick,    sizeof( uint32_t ) } ;
+		case RTX_BUF_GUIDE_ACC: return { c->d_guide_acc, np*6*sizeof( long long ) } ;
 	}
 	throw std::runtime_error( "rtx: unknown buffer id" ) ;
 }
@@ -399,15 +415,26 @@ int rtx_init( int device, rtx_ctx** out ) {
 		c->d_pick = dalloc<uint32_t>( c, 1 ) ;
 		c->d_counter = dalloc<unsigned long long>( c, 1 ) ;
 		c->d_tile_counter = dalloc<uint32_t>( c, 1 ) ;
+		{	// CUDA loads kernels lazily on first launch; do it here so that build and frame
+			// timings measure the kernels, not the loader
+			cudaFuncAttributes fa ;
+			const void* kernels[] = { ( const void* ) k_render<false>, ( const void* ) k_render<true>, ( const void* ) k_primary_hits, ( const void* ) k_trace_rays, ( const void* ) k_pick,
+				( const void* ) k_resolve, ( const void* ) k_resolve_guides, ( const void* ) k_postproc, ( const void* ) k_sum_segments, ( const void* ) k_tri_bounds, ( const void* ) k_thing_bounds,
+				( const void* ) k_bounds_init, ( const void* ) k_bounds_reduce, ( const void* ) k_morton, ( const void* ) k_radix_hist, ( const void* ) k_radix_scan,
+				( const void* ) k_radix_scatter, ( const void* ) k_karras, ( const void* ) k_refit, ( const void* ) k_wide_level, ( const void* ) k_pack_tris } ;
+			for ( const void* k : kernels ) CK( cudaFuncGetAttributes( &fa, k ) ) ;
+		}
 		// the render kernel is persistent: one warp per CTA, as many CTAs as fit
 		// shared memory holds the ray slots, L1 caches the BVH: the carveout decides how many
 		// render warps an SM hosts and how much L1 is left (tunable: RTX_CARVEOUT, percent)
 		int carve = RTX_DEFAULT_CARVEOUT ;
 		if ( const char* e = getenv( "RTX_CARVEOUT" ) ) carve = atoi( e ) ;
-		if ( carve>0 && carve<=100 )
-			CK( cudaFuncSetAttribute( k_render, cudaFuncAttributePreferredSharedMemoryCarveout, carve ) ) ;
+		if ( carve>0 && carve<=100 ) {
+			CK( cudaFuncSetAttribute( k_render<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve ) ) ;
+			CK( cudaFuncSetAttribute( k_render<true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve ) ) ;
+		}
 		int per_sm = 0 ;
-		CK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm, k_render, 32, 0 ) ) ;
+		CK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm, k_render<false>, 32, 0 ) ) ;
 		if ( per_sm<1 ) per_sm = 1 ;
 		c->render_grid = uint32_t( per_sm )*uint32_t( prop.multiProcessorCount ) ;
 		c->d_ovf = dalloc<int32_t>( c, size_t( c->render_grid )*RTX_POOL_R*RTX_POOL_OVF*2 ) ;

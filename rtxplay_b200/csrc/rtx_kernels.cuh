@@ -48,6 +48,8 @@ struct FrameArgs {
 	uint64_t* accum ;    // [4*w*h]  r, g, b fixed-point sums, segments
 	int64_t*  hit_id ;   // [w*h]
 	float*    hit_t ;    // [w*h]
+	uint32_t  guides ;   // fill the guide layers too
+	long long* guide_acc ; // [6*w*h] fixed-point (2^-30) sums: normal xyz, albedo rgb
 } ;
 
 // lane -> pixel: each warp owns an 8x4 tile (primary rays of a warp stay close)
@@ -74,8 +76,10 @@ inline uint32_t tile_grid( uint32_t w, uint32_t h ) {
 #ifndef RTX_MIN_CTAS
 #define RTX_MIN_CTAS 20         // resident render warps per SM the register budget is set for (96 registers)
 #endif
+template <bool GUIDES>
 __global__ void __launch_bounds__( 32, RTX_MIN_CTAS ) k_render( const FrameArgs a, uint32_t* tile_counter, int32_t* ovf_all ) {
 	__shared__ unsigned long long acc[32*3] ;
+	__shared__ unsigned long long gacc[GUIDES ? 32*6 : 1] ;
 	__shared__ uint32_t segs[32] ;
 	const uint32_t lane = threadIdx.x ;
 	const uint32_t lt = ( 1u<<lane )-1u ;
@@ -100,6 +104,8 @@ __global__ void __launch_bounds__( 32, RTX_MIN_CTAS ) k_render( const FrameArgs 
 			break ;
 		const uint32_t x0 = ( tile%tiles_x )*8u, y0 = ( tile/tiles_x )*4u ;
 		acc[lane] = 0 ; acc[lane+32] = 0 ; acc[lane+64] = 0 ; segs[lane] = 0 ;
+		if ( GUIDES )
+			for ( int g = 0 ; g<6 ; g++ ) gacc[lane+32*g] = 0 ;
 		const uint32_t vmask = __ballot_sync( 0xffffffffu, x0+( lane&7u )<a.w && y0+( lane>>3 )<a.h ) ;
 		const uint32_t n_valid = __popc( vmask ) ;
 		const uint32_t total = n_valid*a.spp ;   // paths of this tile: index = sample*n_valid + (rank of pixel)
@@ -162,10 +168,15 @@ __global__ void __launch_bounds__( 32, RTX_MIN_CTAS ) k_render( const FrameArgs 
 					break ;
 				case K_SHADE:
 					if ( j>=0 ) {
-						f3 c ;
-						nk = step_shade( p, slot, a.S, c ) ;
+						f3 c, gn, ga ; bool g ;
+						nk = step_shade( p, slot, a.S, c, g, gn, ga ) ;
 						const uint32_t px = uint32_t( p.i( F_PIX, slot ) ) ;
 						atomicAdd( segs+px, 1u ) ;
+						if ( GUIDES && g ) {
+							const float v[6] = { gn.x, gn.y, gn.z, ga.x, ga.y, ga.z } ;
+							for ( int q = 0 ; q<6 ; q++ )
+								atomicAdd( gacc+32*q+px, ( unsigned long long )( long long )( v[q]*1073741824.f ) ) ;
+						}
 						if ( nk == K_REGEN ) {
 							atomicAdd( acc+px, ( unsigned long long ) tofix( c.x ) ) ;
 							atomicAdd( acc+32+px, ( unsigned long long ) tofix( c.y ) ) ;
@@ -200,6 +211,11 @@ __global__ void __launch_bounds__( 32, RTX_MIN_CTAS ) k_render( const FrameArgs 
 				lo.x += plo.x ; lo.y += plo.y ; hi.x += phi.x ; hi.y += phi.y ;
 			}
 			out[0] = lo ; out[1] = hi ;
+			if ( GUIDES )
+				for ( int g = 0 ; g<6 ; g++ ) {
+					long long* o = a.guide_acc+6*size_t( pix )+g ;
+					*o = ( a.accumulate ? *o : 0ll )+( long long ) gacc[32*g+lane] ;
+				}
 		}
 		__syncwarp() ;
 	}
@@ -274,6 +290,18 @@ __global__ void __launch_bounds__( 256 ) k_resolve( const uint64_t* accum, uint3
 		raw[3*size_t( p )+c] = 0.f>v ? 0.f : v>1.f ? 1.f : v ;
 	}
 	rpp[p] = uint32_t( hi.y ) ;
+}
+
+// guide layers: mean of the fixed-point sums (optx/camera_i.cu:109-113)
+__global__ void __launch_bounds__( 256 ) k_resolve_guides( const long long* gacc, uint32_t npix, uint64_t total_spp, float* normals, float* albedos ) {
+	const uint32_t p = blockIdx.x*blockDim.x+threadIdx.x ;
+	if ( p>=npix )
+		return ;
+	const double n = double( total_spp ) ;
+	for ( int c = 0 ; c<3 ; c++ ) {
+		normals[3*size_t( p )+c] = float( double( gacc[6*size_t( p )+c] )*( 1./1073741824. )/n ) ;
+		albedos[3*size_t( p )+c] = float( double( gacc[6*size_t( p )+3+c] )*( 1./1073741824. )/n ) ;
+	}
 }
 
 // optx/postproc.cu:18-34 (none) and :2-16, 36-47 (sRGB): float3 -> uchar4, truncating

@@ -290,7 +290,11 @@ template <class P> RTX_HD int step_thing( P& p, int slot, const SceneDev& S ) {
 
 // ---- SHADE: the ray is finished.  Returns K_NODE/K_SHADE (path continues with a new ray)
 // or K_REGEN (path ended; `c` is its colour).  rtow.cxx:34-49.
-template <class P> RTX_HD int step_shade( P& p, int slot, const SceneDev& S, f3& c ) {
+// Guide layers: the first diffuse or reflecting hit of a path contributes its normal and
+// albedo (optx/optics_i.cu:97-101, 185-189; refracting hits do not); bit 8 of F_META marks
+// a path that has contributed.  `guide` is set when this call captured them.
+template <class P> RTX_HD int step_shade( P& p, int slot, const SceneDev& S, f3& c, bool& guide, f3& gnormal, f3& galbedo ) {
+	guide = false ;
 	HitRec h ;
 	RTX_COUNT( rays ) ;
 	h.t = p.f( F_T, slot ) ; h.thing = p.i( F_THING, slot ) ; h.prim = p.i( F_PRIM, slot ) ; h.u = p.f( F_U, slot ) ; h.v = p.f( F_V, slot ) ;
@@ -310,12 +314,18 @@ template <class P> RTX_HD int step_shade( P& p, int slot, const SceneDev& S, f3&
 	Pcg rng ;
 	rng.state = uint64_t( uint32_t( p.i( F_RNG0, slot ) ) )|( uint64_t( uint32_t( p.i( F_RNG1, slot ) ) )<<32 ) ;
 	f3 att, out ;
-	if ( ! scatter( S.shade+h.thing, dir, fr, rng, att, out ) )
+	const bool go = scatter( S.shade+h.thing, dir, fr, rng, att, out ) ;
+	uint32_t meta2 = meta ;
+	if ( ! ( meta&256u ) && RTX_LDG( &( S.shade+h.thing )->type ) != 2 ) {
+		guide = true ; gnormal = fr.normal ; galbedo = att ;   // att = the thing's albedo for diffuse / reflect
+		meta2 |= 256u ;
+	}
+	if ( ! go )
 		return K_REGEN ;
 	thr = thr*att ;
 	st3( p, F_THRX, slot, thr ) ;
 	p.si( F_RNG0, slot, int32_t( uint32_t( rng.state ) ) ) ; p.si( F_RNG1, slot, int32_t( uint32_t( rng.state>>32 ) ) ) ;
-	p.si( F_META, slot, int32_t( meta-1u ) ) ;
+	p.si( F_META, slot, int32_t( meta2-1u ) ) ;
 	begin_ray( p, slot, S, fr.p, out ) ;
 	return kind_of( p.i( F_CUR, slot ), -1 ) ;
 }

@@ -18,10 +18,13 @@ class Launcher {
 
 		// additive: stream key and sample window of the frame (defaults: 4711, all samples)
 		void seed( unsigned long long seed ) { seed_ = seed ; }
+		// additive: fill lp_general.normals / albedos (the reference always does; here on request)
+		void guides( bool on ) { guides_ = on ; }
 
 	private:
 		rtx_ctx*           ctx_ ;
 		unsigned long long seed_ ;
+		bool               guides_ = false ;
 
 		void bind() ;
 } ;

@@ -181,6 +181,7 @@ int main( int argc, char* argv[] ) {
 		OptixShaderBindingTable sbt ;
 		Launcher launcher( pipeline, sbt ) ;
 		cg::launcher = &launcher ;
+		launcher.guides( args.param_D( Dns::NONE ) != Dns::NONE ) ;   // guide layers feed the denoiser / -G
 
 		// launch (the reference times ignite + stream destroy, optx/rtwo.cxx:542-546)
 		CUstream cuda_stream ;

@@ -37,7 +37,7 @@ def test_struct_sizes_match_header():
     # rtx_params: 4 u32 + camera (19 floats) + pad + u64 + 3 u32 (+pad)
     assert ctypes.sizeof(_lib.RtxCamera) == 19 * 4
     assert ctypes.sizeof(_lib.RtxOptics) == 24
-    assert ctypes.sizeof(_lib.RtxParams) == 120
+    assert ctypes.sizeof(_lib.RtxParams) == 120          # guides fills the former tail padding
     assert ctypes.sizeof(_lib.RtxStats) == 64
 
 

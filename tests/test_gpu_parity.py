@@ -135,6 +135,26 @@ def test_postproc_matches_reference_transfer(spheres):
     ctx.close()
 
 
+@pytest.mark.parametrize("mode,ndiv", [("analytic", None), ("mesh", 2)])
+def test_guide_layers(spheres, mode, ndiv):
+    """Denoiser guide layers (optx/camera_i.cu:99-113, optx/optics_i.cu:97-101, 185-189): per-pixel
+    means of the first diffuse/reflecting hit's normal and albedo; fixed-point sums equal the oracle's."""
+    ctx, tab, meshes = _ctx(spheres, mode, ndiv)
+    w, h, spp = 96, 64, 4
+    cam = api.camera(aspratio=w / h)
+    ctx.resize(w, h)
+    ctx.render(ctx.params(cam, spp, guides=1))
+    ref = orc.render(orc.F32_PCG, tab, api.camera_table(cam), w, h, spp, 50, meshes=meshes, want_guides=True)
+    assert np.array_equal(ctx.read(api.BUF_GUIDE_ACC), ref["guide"])
+    assert np.array_equal(ctx.read(api.BUF_ACCUM)[..., :3], ref["fix"])          # the frame itself is unchanged
+    nrm = ctx.read(api.BUF_NORMALS)
+    alb = ctx.read(api.BUF_ALBEDOS)
+    assert np.allclose(nrm, ref["guide"][..., :3] / 2. ** 30 / spp, atol=1e-6)
+    assert np.allclose(alb, ref["guide"][..., 3:] / 2. ** 30 / spp, atol=1e-6)
+    assert np.linalg.norm(nrm, axis=2).max() <= 1. + 1e-5 and alb.min() >= 0.
+    ctx.close()
+
+
 def test_picker_and_refit(spheres):
     """optx/simplesm.cxx:1014-1048 picker + Scene::set/update (optx/scene.cxx:198-215, 275-294)."""
     ctx, tab, _ = _ctx(spheres, "analytic")
