@@ -57,6 +57,7 @@ struct Lbvh {           // one built tree: wide traversal nodes + (when kept) th
 
 struct Mesh {
 	bool      analytic = false ;
+	double    bsphere[4] = { 0, 0, 0, 0 } ;   // object-space bounding sphere
 	uint32_t  nv = 0, nt = 0 ;
 	float*    vces = nullptr ;
 	uint32_t* ices = nullptr ;
@@ -84,6 +85,7 @@ struct rtx_ctx {
 	// device scene
 	ThingTrav*  d_trav = nullptr ;
 	ThingShade* d_shade = nullptr ;
+	q4*         d_bsphere = nullptr ;
 	q4*         d_tb_lo = nullptr ;   // per-thing mesh root boxes, then world boxes
 	q4*         d_tb_hi = nullptr ;
 	q4*         d_tp_lo = nullptr ;
@@ -248,15 +250,15 @@ void lbvh_build( rtx_ctx* c, Lbvh& b, const q4* plo, const q4* phi, uint32_t n, 
 void upload_things( rtx_ctx* c ) {
 	const uint32_t n = uint32_t( c->things.size() ) ;
 	if ( n != c->n_things_dev ) {
-		dfree( c, c->d_trav, c->n_things_dev ) ; dfree( c, c->d_shade, c->n_things_dev ) ;
+		dfree( c, c->d_trav, c->n_things_dev ) ; dfree( c, c->d_shade, c->n_things_dev ) ; dfree( c, c->d_bsphere, c->n_things_dev ) ;
 		dfree( c, c->d_tb_lo, c->n_things_dev ) ; dfree( c, c->d_tb_hi, c->n_things_dev ) ;
 		dfree( c, c->d_tp_lo, c->n_things_dev ) ; dfree( c, c->d_tp_hi, c->n_things_dev ) ;
-		c->d_trav = dalloc<ThingTrav>( c, n ) ; c->d_shade = dalloc<ThingShade>( c, n ) ;
+		c->d_trav = dalloc<ThingTrav>( c, n ) ; c->d_shade = dalloc<ThingShade>( c, n ) ; c->d_bsphere = dalloc<q4>( c, n ) ;
 		c->d_tb_lo = dalloc<q4>( c, n ) ; c->d_tb_hi = dalloc<q4>( c, n ) ;
 		c->d_tp_lo = dalloc<q4>( c, n ) ; c->d_tp_hi = dalloc<q4>( c, n ) ;
 		c->n_things_dev = n ;
 	}
-	std::vector<ThingTrav> trav( n ) ; std::vector<ThingShade> shade( n ) ; std::vector<q4> lo( n ), hi( n ) ;
+	std::vector<ThingTrav> trav( n ) ; std::vector<ThingShade> shade( n ) ; std::vector<q4> lo( n ), hi( n ), bs( n ) ;
 	for ( uint32_t k = 0 ; k<n ; k++ ) {
 		const ThingHost& th = c->things[k] ;
 		const Mesh& m = c->meshes[th.mesh] ;
@@ -269,7 +271,9 @@ void upload_things( rtx_ctx* c ) {
 			t.kind = 0 ; s.kind = 0 ;
 			t.inv[0] = double( th.xf[3] ) ; t.inv[1] = double( th.xf[7] ) ; t.inv[2] = double( th.xf[11] ) ; t.inv[3] = double( th.xf[0] ) ;
 			lo[k] = { 0, 0, 0, 0 } ; hi[k] = { 0, 0, 0, 0 } ;
+			bs[k] = { 0.f, 0.f, 0.f, -1.f } ;   // the sphere test itself is the test
 		} else {
+			world_bsphere( th.xf, m.bsphere, &bs[k].x ) ;
 			t.kind = 1 ; s.kind = 1 ;
 			affine_inverse( th.xf, t.inv ) ;
 			t.nodes = m.bvh.nodes ; t.tris = m.tris ; t.n_tris = m.nt ;
@@ -279,6 +283,7 @@ void upload_things( rtx_ctx* c ) {
 	}
 	CK( cudaMemcpyAsync( c->d_trav, trav.data(), sizeof( ThingTrav )*n, cudaMemcpyHostToDevice, c->stream ) ) ;
 	CK( cudaMemcpyAsync( c->d_shade, shade.data(), sizeof( ThingShade )*n, cudaMemcpyHostToDevice, c->stream ) ) ;
+	CK( cudaMemcpyAsync( c->d_bsphere, bs.data(), sizeof( q4 )*n, cudaMemcpyHostToDevice, c->stream ) ) ;
 	CK( cudaMemcpyAsync( c->d_tb_lo, lo.data(), sizeof( q4 )*n, cudaMemcpyHostToDevice, c->stream ) ) ;
 	CK( cudaMemcpyAsync( c->d_tb_hi, hi.data(), sizeof( q4 )*n, cudaMemcpyHostToDevice, c->stream ) ) ;
 	CK( cudaStreamSynchronize( c->stream ) ) ;   // the host vectors go out of scope
@@ -292,7 +297,7 @@ void upload_things( rtx_ctx* c ) {
 SceneDev scene_dev( const rtx_ctx* c ) {
 	SceneDev S ;
 	S.tlas_nodes = c->tlas.nodes ; S.tlas_order = c->tlas.order ;
-	S.trav = c->d_trav ; S.shade = c->d_shade ; S.n_things = c->n_things_dev ;
+	S.trav = c->d_trav ; S.shade = c->d_shade ; S.bsphere = c->d_bsphere ; S.n_things = c->n_things_dev ;
 	return S ;
 }
 
@@ -457,7 +462,7 @@ void rtx_shutdown( rtx_ctx* c ) {
 		lbvh_free( c, m.bvh ) ;
 	}
 	lbvh_free( c, c->tlas ) ;
-	dfree( c, c->d_trav, c->n_things_dev ) ; dfree( c, c->d_shade, c->n_things_dev ) ;
+	dfree( c, c->d_trav, c->n_things_dev ) ; dfree( c, c->d_shade, c->n_things_dev ) ; dfree( c, c->d_bsphere, c->n_things_dev ) ;
 	dfree( c, c->d_tb_lo, c->n_things_dev ) ; dfree( c, c->d_tb_hi, c->n_things_dev ) ;
 	dfree( c, c->d_tp_lo, c->n_things_dev ) ; dfree( c, c->d_tp_hi, c->n_things_dev ) ;
 	free_frame( c ) ;
@@ -479,6 +484,7 @@ int rtx_mesh_create( rtx_ctx* c, const float* xyz, uint32_t nv, const uint32_t* 
 		if ( idx[k]>=nv ) throw std::runtime_error( "rtx_mesh_create: index out of bounds" ) ;   // optx/object.cxx:62-67
 	Mesh m ;
 	m.nv = nv ; m.nt = nt ;
+	mesh_bsphere( xyz, nv, m.bsphere ) ;
 	m.vces = dalloc<float>( c, 3*size_t( nv ) ) ; m.ices = dalloc<uint32_t>( c, 3*size_t( nt ) ) ; m.tris = dalloc<q4>( c, RTX_TRI_RECS*size_t( nt ) ) ;
 	CK( cudaMemcpyAsync( m.vces, xyz, sizeof( float )*3*nv, cudaMemcpyHostToDevice, c->stream ) ) ;
 	CK( cudaMemcpyAsync( m.ices, idx, sizeof( uint32_t )*3*size_t( nt ), cudaMemcpyHostToDevice, c->stream ) ) ;

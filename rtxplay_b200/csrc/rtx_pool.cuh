@@ -257,6 +257,11 @@ template <class P> RTX_HD int step_thing( P& p, int slot, const SceneDev& S ) {
 	const ThingTrav* tt = S.trav+k ;
 	RTX_COUNT( things ) ;
 	const f3 o = ld3( p, F_OX, slot ), d = ld3( p, F_DX, slot ) ;
+	if ( bsphere_miss( ldq( S.bsphere+k ), o, d, 1e-3f, p.f( F_T, slot ) ) ) {
+		RTX_COUNT( spheres ) ;   // (harness: counts culled visits)
+		cur = pop_next( p, slot, S, sp, level ) ;
+		return finish_step( p, slot, cur, sp, level ) ;
+	}
 	const double m0 = RTX_LDG( tt->inv+0 ), m1 = RTX_LDG( tt->inv+1 ), m2 = RTX_LDG( tt->inv+2 ), m3 = RTX_LDG( tt->inv+3 ) ;
 	if ( RTX_LDG( &tt->kind ) == 0 ) {
 		double td ;

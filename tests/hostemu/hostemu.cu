@@ -169,12 +169,13 @@ void build_tree( const std::vector<q4>& plo, const std::vector<q4>& phi, Tree& T
 	T.root_lo = blo[0] ; T.root_hi = bhi[0] ;
 }
 
-struct EmuMesh { std::vector<float> vces ; std::vector<uint32_t> ices ; std::vector<q4> tris ; Tree tree ; } ;
+struct EmuMesh { std::vector<float> vces ; std::vector<uint32_t> ices ; std::vector<q4> tris ; Tree tree ; double bsphere[4] ; } ;
 
 struct EmuScene {
 	std::vector<EmuMesh>    meshes ;
 	std::vector<ThingTrav>  trav ;
 	std::vector<ThingShade> shade ;
+	std::vector<q4>         bsphere ;
 	Tree                    tlas ;
 	SceneDev                S ;
 } ;
@@ -187,6 +188,7 @@ void build_scene( EmuScene& E, const double* things, int n_things, int n_meshes,
 		EmuMesh& m = E.meshes[q] ;
 		m.vces.assign( vces[q], vces[q]+3*size_t( nv[q] ) ) ;
 		m.ices.assign( ices[q], ices[q]+3*size_t( nt[q] ) ) ;
+		mesh_bsphere( vces[q], nv[q], m.bsphere ) ;
 		std::vector<q4> plo( nt[q] ), phi( nt[q] ) ;
 		for ( uint32_t f = 0 ; f<nt[q] ; f++ ) {
 			const float* a = &m.vces[3*size_t( m.ices[3*f] )] ; const float* b = &m.vces[3*size_t( m.ices[3*f+1] )] ; const float* c = &m.vces[3*size_t( m.ices[3*f+2] )] ;
@@ -203,7 +205,7 @@ void build_scene( EmuScene& E, const double* things, int n_things, int n_meshes,
 			m.tris[RTX_TRI_RECS*size_t( j )+2] = { c[0]-a[0], c[1]-a[1], c[2]-a[2], 0.f } ;
 		}
 	}
-	E.trav.resize( n_things ) ; E.shade.resize( n_things ) ;
+	E.trav.resize( n_things ) ; E.shade.resize( n_things ) ; E.bsphere.resize( n_things ) ;
 	std::vector<q4> plo( n_things ), phi( n_things ) ;
 	for ( int k = 0 ; k<n_things ; k++ ) {
 		const double* row = things+size_t( k )*TH_STRIDE ;
@@ -215,6 +217,7 @@ void build_scene( EmuScene& E, const double* things, int n_things, int n_meshes,
 		s.fuzz = float( row[TH_FUZZ] ) ; s.index = float( row[TH_INDEX] ) ; s.type = int( row[TH_TYPE] ) ;
 		if ( int( row[TH_KIND] ) == 0 ) {
 			t.kind = 0 ; s.kind = 0 ;
+			E.bsphere[k] = { 0.f, 0.f, 0.f, -1.f } ;
 			t.inv[0] = double( xf[3] ) ; t.inv[1] = double( xf[7] ) ; t.inv[2] = double( xf[11] ) ; t.inv[3] = double( xf[0] ) ;
 			const double r = fabs( t.inv[3] ) ;
 			plo[k] = { float( t.inv[0]-r )-1e-3f, float( t.inv[1]-r )-1e-3f, float( t.inv[2]-r )-1e-3f, 0.f } ;
@@ -222,6 +225,7 @@ void build_scene( EmuScene& E, const double* things, int n_things, int n_meshes,
 		} else {
 			const EmuMesh& m = E.meshes[int( row[TH_MESH] )] ;
 			t.kind = 1 ; s.kind = 1 ;
+			world_bsphere( xf, m.bsphere, &E.bsphere[k].x ) ;
 			affine_inverse( xf, t.inv ) ;
 			t.nodes = m.tree.nodes.data() ; t.tris = m.tris.data() ; t.n_tris = uint32_t( m.ices.size()/3 ) ;
 			s.vces = m.vces.data() ; s.ices = m.ices.data() ;
@@ -238,7 +242,7 @@ void build_scene( EmuScene& E, const double* things, int n_things, int n_meshes,
 	}
 	if ( n_things ) build_tree( plo, phi, E.tlas, 1 ) ;
 	E.S.tlas_nodes = E.tlas.nodes.data() ; E.S.tlas_order = E.tlas.order.data() ;
-	E.S.trav = E.trav.data() ; E.S.shade = E.shade.data() ; E.S.n_things = uint32_t( n_things ) ;
+	E.S.trav = E.trav.data() ; E.S.shade = E.shade.data() ; E.S.bsphere = E.bsphere.data() ; E.S.n_things = uint32_t( n_things ) ;
 }
 
 } // namespace
