@@ -19,8 +19,17 @@
 
 #if defined( __CUDACC__ )
 #define RTX_HD __host__ __device__ __forceinline__
+// big, rarely executed pieces (shading frame, scattering, ray generation) are real calls:
+// the render kernel is ~50 KB of code run by ~20 independent warps per SM, and instruction
+// fetch was its top stall (ncu: stall_no_inst 28 %)
+#if defined( RTX_INLINE_ALL )
+#define RTX_HD_CALL __host__ __device__ __forceinline__
+#else
+#define RTX_HD_CALL __host__ __device__ __noinline__
+#endif
 #else
 #define RTX_HD inline
+#define RTX_HD_CALL inline
 #endif
 
 #if defined( __CUDA_ARCH__ )
@@ -301,11 +310,12 @@ RTX_HD bool better( float t, int32_t thing, int32_t prim, const HitRec& best ) {
 // FMA and an approximate reciprocal are used on purpose -- it never decides a result.
 #define RTX_SLACK 1.0000038f
 RTX_HD float safe_rcp( float d ) {
-	const float big = 1e30f ;
+	// 1/d clamped to +-1e30: a zero component gives a huge finite slope instead of inf, so
+	// that o*idir and the slab products stay finite (no inf-inf, no 0*inf)
 #if defined( __CUDA_ARCH__ )
-	return fabsf( d )>1e-30f ? __fdividef( 1.f, d ) : ( d<0.f ? -big : big ) ;   // -0.f counts as +
+	return fminf( fmaxf( __fdividef( 1.f, d ), -1e30f ), 1e30f ) ;
 #else
-	return fabsf( d )>1e-30f ? 1.f/d : ( d<0.f ? -big : big ) ;
+	return fminf( fmaxf( 1.f/d, -1e30f ), 1e30f ) ;
 #endif
 }
 // entry distance of the ray into box (lo,hi), or +inf when it misses [tmin, tbest]
@@ -485,7 +495,7 @@ RTX_HD void closest_brute( const SceneDev& S, const f3& o, const f3& d, float tm
 // ----------------------------------------------------------------------------- shading frame
 // sphere.h:40-45 (analytic) / optx/optics_i.cu:40-82, :259-267 (mesh), in double,
 // rounded once
-RTX_HD void frame_of( const SceneDev& S, const HitRec& h, const f3& o, const f3& d, float tmin, Frame& fr ) {
+RTX_HD_CALL void frame_of( const SceneDev& S, const HitRec& h, const f3& o, const f3& d, float tmin, Frame& fr ) {
 	const ThingShade* ts = S.shade+h.thing ;
 	double m[12] ;
 	for ( int j = 0 ; j<12 ; j++ ) m[j] = RTX_LDG( ts->xf+j ) ;
@@ -536,7 +546,7 @@ RTX_HD float schlick( float cos_theta, float ratio ) {                          
 
 // optics.h:15-24 (Diffuse), :34-40 (Reflect), :51-68 (Refract).  Returns false when
 // the path is absorbed.
-RTX_HD bool scatter( const ThingShade* ts, const f3& dir, const Frame& fr, Pcg& rng, f3& attened, f3& out ) {
+RTX_HD_CALL bool scatter( const ThingShade* ts, const f3& dir, const Frame& fr, Pcg& rng, f3& attened, f3& out ) {
 	const int32_t type = RTX_LDG( &ts->type ) ;
 	if ( type == 0 ) {
 		f3 dnew = fr.normal+rng.rndVon1sphere() ;
@@ -574,7 +584,7 @@ RTX_HD f3 sky( const f3& dir ) {
 }
 
 // rtow.cxx:112-113 + camera.h:25-31
-RTX_HD void primary_ray( const CameraDev& cam, uint32_t x, uint32_t y, uint32_t w, uint32_t h, Pcg& rng, f3& ori, f3& dir ) {
+RTX_HD_CALL void primary_ray( const CameraDev& cam, uint32_t x, uint32_t y, uint32_t w, uint32_t h, Pcg& rng, f3& ori, f3& dir ) {
 	const float s = 2.f*( float( x )+rng.rnd() )/float( w-1 )-1.f ;
 	const float t = 2.f*( float( y )+rng.rnd() )/float( h-1 )-1.f ;
 	const f3 r = ( cam.aperture/2.f )*rng.rndVin1disk() ;
