@@ -275,6 +275,7 @@ void upload_things( rtx_ctx* c ) {
 		} else {
 			world_bsphere( th.xf, m.bsphere, &bs[k].x ) ;
 			t.kind = 1 ; s.kind = 1 ;
+			t.diag = s.diag = ( th.xf[1] == 0.f && th.xf[2] == 0.f && th.xf[4] == 0.f && th.xf[6] == 0.f && th.xf[8] == 0.f && th.xf[9] == 0.f ) ? 1 : 0 ;
 			affine_inverse( th.xf, t.inv ) ;
 			t.nodes = m.bvh.nodes ; t.tris = m.tris ; t.n_tris = m.nt ;
 			s.vces = m.vces ; s.ices = m.ices ;

@@ -91,6 +91,14 @@ RTX_HD d3 xfpoint( const double* m, const d3& p ) {
 RTX_HD d3 xfvec( const double* m, const d3& p ) {
 	return mk3( p.x*m[0]+p.y*m[1]+p.z*m[2], p.x*m[4]+p.y*m[5]+p.z*m[6], p.x*m[8]+p.y*m[9]+p.z*m[10] ) ;
 }
+// the same maps when the off-diagonal terms are zero: the dropped products are +-0 and adding
+// them changes no value, so these give the bits of the general form with a third of the work
+RTX_HD d3 xfpoint_diag( double m0, double m3, double m5, double m7, double m10, double m11, const d3& p ) {
+	return mk3( p.x*m0+m3, p.y*m5+m7, p.z*m10+m11 ) ;
+}
+RTX_HD d3 xfvec_diag( double m0, double m5, double m10, const d3& p ) {
+	return mk3( p.x*m0, p.y*m5, p.z*m10 ) ;
+}
 
 // ----------------------------------------------------------------------------- random stream
 // Stream of path (pixel, sample) = PCG32 (XSH-RR 64/32) started at a splitmix64 hash of
@@ -153,7 +161,8 @@ struct ThingTrav {
 	const q4*  tris ;      // mesh triangles in leaf order: (v0, asfloat(prim)), (e1,-), (e2,-), pad
 	int32_t    kind ;      // 0 analytic sphere, 1 mesh instance
 	uint32_t   n_tris ;
-	int32_t    pad[2] ;
+	int32_t    diag ;      // 1: the transform is a per-axis scale + translation (the off-diagonal terms are zero)
+	int32_t    pad ;
 } ;
 
 // per-thing record read by shading (144 bytes)
@@ -163,7 +172,7 @@ struct ThingShade {
 	float           index ;
 	int32_t         type ;    // rtx_optics type
 	int32_t         kind ;
-	int32_t         pad ;
+	int32_t         diag ;    // as in ThingTrav
 	const float*    vces ;    // mesh vertices (xyz) and indices as uploaded
 	const uint32_t* ices ;
 } ;
@@ -440,13 +449,21 @@ RTX_HD void closest( const SceneDev& S, const f3& o, const f3& d, float tmin, St
 					}
 				} else {
 					// enter the mesh: object-space ray, origin in double carried as hi+lo
-					double m[12] ;
-					m[0] = m0 ; m[1] = m1 ; m[2] = m2 ; m[3] = m3 ;
-					for ( int j = 4 ; j<12 ; j++ ) m[j] = RTX_LDG( tt->inv+j ) ;
-					const d3 od = xfpoint( m, wide( o ) ) ;
+					d3 od, ddd ;
+					if ( RTX_LDG( &tt->diag ) ) {
+						const double m5 = RTX_LDG( tt->inv+5 ), m7 = RTX_LDG( tt->inv+7 ), m10 = RTX_LDG( tt->inv+10 ), m11 = RTX_LDG( tt->inv+11 ) ;
+						od = xfpoint_diag( m0, m3, m5, m7, m10, m11, wide( o ) ) ;
+						ddd = xfvec_diag( m0, m5, m10, wide( d ) ) ;
+					} else {
+						double m[12] ;
+						m[0] = m0 ; m[1] = m1 ; m[2] = m2 ; m[3] = m3 ;
+						for ( int j = 4 ; j<12 ; j++ ) m[j] = RTX_LDG( tt->inv+j ) ;
+						od = xfpoint( m, wide( o ) ) ;
+						ddd = xfvec( m, wide( d ) ) ;
+					}
 					ohi = narrow( od ) ;
 					olo = narrow( od-wide( ohi ) ) ;
-					dd  = narrow( xfvec( m, wide( d ) ) ) ;
+					dd  = narrow( ddd ) ;
 					idir = mk3( safe_rcp( dd.x ), safe_rcp( dd.y ), safe_rcp( dd.z ) ) ;
 					ood  = mk3( ohi.x*idir.x, ohi.y*idir.y, ohi.z*idir.z ) ;
 					nodes = ldptr( &tt->nodes ) ;
@@ -518,7 +535,14 @@ RTX_HD_CALL void frame_of( const SceneDev& S, const HitRec& h, const f3& o, cons
 	const d3 a = mk3( double( RTX_LDG( vces+3*size_t( i0 ) ) ), double( RTX_LDG( vces+3*size_t( i0 )+1 ) ), double( RTX_LDG( vces+3*size_t( i0 )+2 ) ) ) ;
 	const d3 b = mk3( double( RTX_LDG( vces+3*size_t( i1 ) ) ), double( RTX_LDG( vces+3*size_t( i1 )+1 ) ), double( RTX_LDG( vces+3*size_t( i1 )+2 ) ) ) ;
 	const d3 c = mk3( double( RTX_LDG( vces+3*size_t( i2 ) ) ), double( RTX_LDG( vces+3*size_t( i2 )+1 ) ), double( RTX_LDG( vces+3*size_t( i2 )+2 ) ) ) ;
-	const d3 A = xfpoint( m, a ), B = xfpoint( m, b ), C = xfpoint( m, c ) ;
+	d3 A, B, C ;
+	if ( RTX_LDG( &ts->diag ) ) {
+		A = xfpoint_diag( m[0], m[3], m[5], m[7], m[10], m[11], a ) ;
+		B = xfpoint_diag( m[0], m[3], m[5], m[7], m[10], m[11], b ) ;
+		C = xfpoint_diag( m[0], m[3], m[5], m[7], m[10], m[11], c ) ;
+	} else {
+		A = xfpoint( m, a ) ; B = xfpoint( m, b ) ; C = xfpoint( m, c ) ;
+	}
 	const float w = 1.f-h.u-h.v ;
 	const d3 p = double( w )*A+double( h.u )*B+double( h.v )*C ;
 	d3 N = unitV( cross( B-A, C-A ) ) ;

@@ -190,8 +190,11 @@ __global__ void __launch_bounds__( 32, RTX_MIN_CTAS ) k_render( const FrameArgs 
 					next += __popc( want ) ;
 					if ( j>=0 ) {
 						if ( idx<total ) {
-							const uint32_t px = __fns( vmask, 0, int( idx%n_valid )+1 ) ;   // idx%n_valid-th valid pixel of the tile
-							nk = step_regen( p, slot, a.S, a.cam, x0+( px&7u ), y0+( px>>3 ), a.w, a.h, px, a.seed, a.sample0+( idx/n_valid )*a.sample_stride, a.depth ) ;
+							// path idx -> (sample, pixel of the tile); tiles cut by the image border take the slow way
+							uint32_t px, smp ;
+							if ( n_valid == 32u ) { px = idx&31u ; smp = idx>>5 ; }
+							else { px = __fns( vmask, 0, int( idx%n_valid )+1 ) ; smp = idx/n_valid ; }
+							nk = step_regen( p, slot, a.S, a.cam, x0+( px&7u ), y0+( px>>3 ), a.w, a.h, px, a.seed, a.sample0+smp*a.sample_stride, a.depth ) ;
 						} else
 							nk = K_DONE ;
 					}

@@ -277,13 +277,21 @@ template <class P> RTX_HD int step_thing( P& p, int slot, const SceneDev& S ) {
 		return finish_step( p, slot, cur, sp, level ) ;
 	}
 	// enter the mesh: object-space ray, origin in double carried as hi+lo
-	double m[12] ;
-	m[0] = m0 ; m[1] = m1 ; m[2] = m2 ; m[3] = m3 ;
-	for ( int j = 4 ; j<12 ; j++ ) m[j] = RTX_LDG( tt->inv+j ) ;
-	const d3 od = xfpoint( m, wide( o ) ) ;
+	d3 od, ddd ;
+	if ( RTX_LDG( &tt->diag ) ) {
+		const double m5 = RTX_LDG( tt->inv+5 ), m7 = RTX_LDG( tt->inv+7 ), m10 = RTX_LDG( tt->inv+10 ), m11 = RTX_LDG( tt->inv+11 ) ;
+		od = xfpoint_diag( m0, m3, m5, m7, m10, m11, wide( o ) ) ;
+		ddd = xfvec_diag( m0, m5, m10, wide( d ) ) ;
+	} else {
+		double m[12] ;
+		m[0] = m0 ; m[1] = m1 ; m[2] = m2 ; m[3] = m3 ;
+		for ( int j = 4 ; j<12 ; j++ ) m[j] = RTX_LDG( tt->inv+j ) ;
+		od = xfpoint( m, wide( o ) ) ;
+		ddd = xfvec( m, wide( d ) ) ;
+	}
 	const f3 ohi = narrow( od ) ;
 	const f3 olo = narrow( od-wide( ohi ) ) ;
-	const f3 dd  = narrow( xfvec( m, wide( d ) ) ) ;
+	const f3 dd  = narrow( ddd ) ;
 	const f3 idir = mk3( safe_rcp( dd.x ), safe_rcp( dd.y ), safe_rcp( dd.z ) ) ;
 	st3( p, F_HX, slot, ohi ) ; st3( p, F_LX, slot, olo ) ; st3( p, F_EX, slot, dd ) ;
 	st3( p, F_IX, slot, idir ) ; st3( p, F_QX, slot, mk3( ohi.x*idir.x, ohi.y*idir.y, ohi.z*idir.z ) ) ;

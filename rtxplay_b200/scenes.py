@@ -73,8 +73,33 @@ def grid_field(n_side, seed=2, ndiv=6):
 def xf_of(sp):
     """Row-major 3x4 transform of a sphere instance: uniform scale + translation
     (optx/rtwo.cxx:159-165)."""
+    if "xf" in sp:                      # a general affine instance transform
+        return np.asarray(sp["xf"], dtype=np.float32).reshape(12)
     r, (cx, cy, cz) = sp["radius"], sp["center"]
     return np.array([r, 0, 0, cx, 0, r, 0, cy, 0, 0, r, cz], dtype=np.float32)
+
+
+def affine_mix(seed=7, n=24):
+    """A small scene whose mesh instances carry general affine transforms (rotation, non-uniform
+    scale, shear) -- exercises the non-diagonal transform path; mesh mode only."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    s = [_sphere((0., -1000., 0.), 1000., api.DIFFUSE, (.5, .5, .5), ndiv=3)]
+    for k in range(n):
+        c = np.array([rng.uniform(-4, 4), rng.uniform(.4, 1.5), rng.uniform(-4, 4)])
+        ax = rng.normal(size=3)
+        ax /= np.linalg.norm(ax)
+        ang = rng.uniform(0, np.pi)
+        K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+        R = np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
+        S = np.diag(rng.uniform(.15, .5, 3))
+        H = np.eye(3)
+        H[0, 1] = rng.uniform(-.3, .3)
+        M = R @ S @ H
+        t = int(rng.integers(0, 3))
+        sp = _sphere(tuple(c), .3, t, tuple(rng.uniform(.2, .9, 3)), fuzz=rng.uniform(0, .4), index=1.5, ndiv=2)
+        sp["xf"] = np.concatenate([M, c[:, None]], axis=1).astype(np.float32).reshape(12)
+        s.append(sp)
+    return s
 
 
 def table(spheres, mode="analytic", ndiv=None):

@@ -225,6 +225,7 @@ void build_scene( EmuScene& E, const double* things, int n_things, int n_meshes,
 		} else {
 			const EmuMesh& m = E.meshes[int( row[TH_MESH] )] ;
 			t.kind = 1 ; s.kind = 1 ;
+			t.diag = s.diag = ( xf[1] == 0.f && xf[2] == 0.f && xf[4] == 0.f && xf[6] == 0.f && xf[8] == 0.f && xf[9] == 0.f ) ? 1 : 0 ;
 			world_bsphere( xf, m.bsphere, &E.bsphere[k].x ) ;
 			affine_inverse( xf, t.inv ) ;
 			t.nodes = m.tree.nodes.data() ; t.tris = m.tris.data() ; t.n_tris = uint32_t( m.ices.size()/3 ) ;

@@ -110,6 +110,20 @@ def test_cuda_core_on_host_equals_float_mirror(mode, ndiv, pool):
     assert np.array_equal(f["fix"], e["fix"])
 
 
+def test_general_affine_instances_on_host():
+    """Rotated / sheared / non-uniformly scaled mesh instances (the non-diagonal transform path)."""
+    sp = scenes.affine_mix()
+    tab, meshes = scenes.table(sp, "mesh")
+    cam = api.camera_table(api.camera(eye=(9., 3., 6.), aspratio=1.5, aperture=.05, fostance=9.))
+    w, h, spp = 60, 40, 2
+    f = orc.render(orc.F32_PCG, tab, cam, w, h, spp, 50, want_first=True, meshes=meshes)
+    e = hostemu.render(tab, cam, w, h, spp, 50, meshes=meshes)
+    assert (f["first_id"] >= 0).mean() > .3
+    assert np.array_equal(f["first_id"], e["first_id"])
+    assert np.array_equal(f["rpp"], e["rpp"])
+    assert np.array_equal(f["fix"], e["fix"])
+
+
 def test_lbvh_traversal_equals_exhaustive_scan_on_host():
     sp = scenes.book1(seed=5)
     tab, meshes = scenes.table(sp, "mesh", 3)

@@ -38,6 +38,25 @@ def test_frame_equals_float_mirror(spheres, mode, ndiv, w, h, spp):
     ctx.close()
 
 
+def test_general_affine_instances():
+    """Rotated / sheared / non-uniformly scaled mesh instances against the float mirror."""
+    sp = scenes.affine_mix()
+    ctx = api.Context(0)
+    tab, meshes = scenes.load(ctx, sp, "mesh")
+    w, h, spp = 150, 100, 4
+    cam = api.camera(eye=(9., 3., 6.), aspratio=w / h, aperture=.05, fostance=9.)
+    ctx.resize(w, h)
+    p = ctx.params(cam, spp)
+    ctx.render(p)
+    acc = ctx.read(api.BUF_ACCUM)
+    ids, _ = ctx.primary_hits(p)
+    ref = orc.render(orc.F32_PCG, tab, api.camera_table(cam), w, h, spp, 50, want_first=True, meshes=meshes)
+    assert np.array_equal(ids, ref["first_id"])
+    assert np.array_equal(acc[..., 3].astype(np.uint32), ref["rpp"])
+    assert np.array_equal(acc[..., :3], ref["fix"])
+    ctx.close()
+
+
 def test_first_hit_ids_full_frame_analytic(spheres):
     """BASELINE.json: primary-ray first-hit ids bit-exact on an identical ray set, 1200x800."""
     ctx, tab, _ = _ctx(spheres, "analytic")
