@@ -351,8 +351,12 @@ void do_render( rtx_ctx* c, const rtx_params* p, bool resolve ) {
 	c->guides_valid = a.guides != 0 ;
 	CK( cudaEventRecord( c->ev0, c->stream ) ) ;
 	if ( a.depth>255u ) throw std::runtime_error( "rtx: depth above 255 is not supported" ) ;
-	const uint32_t n_tiles = ( ( a.w+7u )>>3 )*( ( a.h+3u )>>2 ) ;
+	const uint32_t n_tiles = ( ( a.w+7u )>>3 )*( ( a.h+3u )>>2 )*( ( a.spp+RTX_UNIT_SPP-1u )/RTX_UNIT_SPP ) ;   // work units
 	CK( cudaMemsetAsync( c->d_tile_counter, 0, sizeof( uint32_t ), c->stream ) ) ;
+	if ( ! a.accumulate ) {   // paths add into the buffers with atomics: start from zero (optx/camera_i.cu:52)
+		CK( cudaMemsetAsync( c->d_accum, 0, sizeof( uint64_t )*4*size_t( a.w )*a.h, c->stream ) ) ;
+		if ( a.guides ) CK( cudaMemsetAsync( c->d_guide_acc, 0, sizeof( long long )*6*size_t( a.w )*a.h, c->stream ) ) ;
+	}
 	if ( a.guides ) k_render<true><<<min( c->render_grid, n_tiles ), 32, 0, c->stream>>>( a, c->d_tile_counter, c->d_ovf ) ;
 	else            k_render<false><<<min( c->render_grid, n_tiles ), 32, 0, c->stream>>>( a, c->d_tile_counter, c->d_ovf ) ;
 	c->launches += 1 ;

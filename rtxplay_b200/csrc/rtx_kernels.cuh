@@ -66,9 +66,13 @@ inline uint32_t tile_grid( uint32_t w, uint32_t h ) {
 	return ( warps*32u+RTX_BLOCK-1u )/RTX_BLOCK ;
 }
 
-// The path tracer (see rtx_pool.cuh): one warp per CTA, persistent; a warp takes an 8x4 pixel
-// tile, traces all its paths -- 32*spp of them, RTX_K*32 in flight -- and writes the tile's
-// fixed-point sums.  Tiles are handed out through a global counter.
+// The path tracer (see rtx_pool.cuh): one warp per CTA, persistent.  Work is handed out in
+// small units -- an 8x4 pixel tile x RTX_UNIT_SPP samples = up to 512 paths -- through a
+// global counter; a warp streams from one unit straight into the next (a lane whose path
+// ends takes the next path of the warp's current unit, whichever tile that is), so no lane
+// idles at tile ends and the kernel's tail is one unit, not one tile of 16 000 paths.  A
+// finished path adds its fixed-point colour and its segment count to the pixel with global
+// integer atomics: order free, bit-reproducible, and no per-tile buffers.
 #define RTX_POOL_R ( 32*RTX_K )
 #ifndef RTX_STICKY
 #define RTX_STICKY 14          // keep doing node steps while at least this many lanes have one
@@ -76,11 +80,9 @@ inline uint32_t tile_grid( uint32_t w, uint32_t h ) {
 #ifndef RTX_MIN_CTAS
 #define RTX_MIN_CTAS 20         // resident render warps per SM the register budget is set for (96 registers)
 #endif
+#define RTX_UNIT_SPP 16u
 template <bool GUIDES>
-__global__ void __launch_bounds__( 32, RTX_MIN_CTAS ) k_render( const FrameArgs a, uint32_t* tile_counter, int32_t* ovf_all ) {
-	__shared__ unsigned long long acc[32*3] ;
-	__shared__ unsigned long long gacc[GUIDES ? 32*6 : 1] ;
-	__shared__ uint32_t segs[32] ;
+__global__ void __launch_bounds__( 32, RTX_MIN_CTAS ) k_render( const FrameArgs a, uint32_t* unit_counter, int32_t* ovf_all ) {
 	const uint32_t lane = threadIdx.x ;
 	const uint32_t lt = ( 1u<<lane )-1u ;
 #if defined( RTX_REGPOOL )
@@ -95,132 +97,131 @@ __global__ void __launch_bounds__( 32, RTX_MIN_CTAS ) k_render( const FrameArgs 
 	p.ovf = ovf_all+size_t( blockIdx.x )*RTX_POOL_R*RTX_POOL_OVF*2 ;
 #endif
 	const uint32_t tiles_x = ( a.w+7u )>>3, tiles_y = ( a.h+3u )>>2, n_tiles = tiles_x*tiles_y ;
+	const uint32_t n_chunks = ( a.spp+RTX_UNIT_SPP-1u )/RTX_UNIT_SPP ;
+	const uint32_t n_units = n_tiles*n_chunks ;   // unit u: chunk u/n_tiles of tile u%n_tiles
+	unsigned long long* accum = reinterpret_cast<unsigned long long*>( a.accum ) ;
+	unsigned long long* guide = reinterpret_cast<unsigned long long*>( a.guide_acc ) ;
+
+	// the warp's current unit (uniform over the warp)
+	uint32_t unit_x0 = 0, unit_y0 = 0, unit_s0 = 0, unit_pos = 0, unit_left = 0 ;
+	bool exhausted = false ;
+
+	int kinds[RTX_K] ;
+#pragma unroll
+	for ( int j = 0 ; j<RTX_K ; j++ ) kinds[j] = K_REGEN ;
 
 	while ( true ) {
-		uint32_t tile = 0 ;
-		if ( lane == 0 ) tile = atomicAdd( tile_counter, 1u ) ;
-		tile = __shfl_sync( 0xffffffffu, tile, 0 ) ;
-		if ( tile>=n_tiles )
-			break ;
-		const uint32_t x0 = ( tile%tiles_x )*8u, y0 = ( tile/tiles_x )*4u ;
-		acc[lane] = 0 ; acc[lane+32] = 0 ; acc[lane+64] = 0 ; segs[lane] = 0 ;
-		if ( GUIDES )
-			for ( int g = 0 ; g<6 ; g++ ) gacc[lane+32*g] = 0 ;
-		const uint32_t vmask = __ballot_sync( 0xffffffffu, x0+( lane&7u )<a.w && y0+( lane>>3 )<a.h ) ;
-		const uint32_t n_valid = __popc( vmask ) ;
-		const uint32_t total = n_valid*a.spp ;   // paths of this tile: index = sample*n_valid + (rank of pixel)
-		uint32_t next = 0 ;
-		int kinds[RTX_K] ;
-#pragma unroll
-		for ( int j = 0 ; j<RTX_K ; j++ ) kinds[j] = K_REGEN ;
-		__syncwarp() ;
-
-		while ( true ) {
-			// vote: which step kind can most lanes take?
+		// vote: which step kind can most lanes take?
 #if RTX_K == 1
-			// one ray per lane: lanes of equal kind find each other (match), the largest group
-			// wins (warp-wide max of size<<3|kind)
-			const uint32_t peers = __match_any_sync( 0xffffffffu, kinds[0] ) ;
-			const int kind = int( __reduce_max_sync( 0xffffffffu, kinds[0] == K_DONE ? 0u : ( uint32_t( __popc( peers ) )<<3 )|uint32_t( kinds[0] ) )&7u ) ;
+		// one ray per lane: lanes of equal kind find each other (match), the largest group
+		// wins (warp-wide max of size<<3|kind)
+		const uint32_t peers = __match_any_sync( 0xffffffffu, kinds[0] ) ;
+		const int kind = int( __reduce_max_sync( 0xffffffffu, kinds[0] == K_DONE ? 0u : ( uint32_t( __popc( peers ) )<<3 )|uint32_t( kinds[0] ) )&7u ) ;
 #else
-			uint32_t mine = 0 ;
+		uint32_t mine = 0 ;
 #pragma unroll
-			for ( int j = 0 ; j<RTX_K ; j++ ) mine |= 1u<<kinds[j] ;
-			int kind = K_DONE ; int most = 0 ;
+		for ( int j = 0 ; j<RTX_K ; j++ ) mine |= 1u<<kinds[j] ;
+		int kind = K_DONE ; int most = 0 ;
 #pragma unroll
-			for ( int k = 1 ; k<K_KINDS ; k++ ) {
-				const int n = __popc( __ballot_sync( 0xffffffffu, ( mine>>k )&1u ) ) ;
-				if ( n>most ) { most = n ; kind = k ; }
-			}
+		for ( int k = 1 ; k<K_KINDS ; k++ ) {
+			const int n = __popc( __ballot_sync( 0xffffffffu, ( mine>>k )&1u ) ) ;
+			if ( n>most ) { most = n ; kind = k ; }
+		}
 #endif
-			if ( kind == K_DONE )
+		if ( kind == K_DONE )
+			break ;
+		int j = -1 ;
+#pragma unroll
+		for ( int jj = RTX_K-1 ; jj>=0 ; jj-- ) if ( kinds[jj] == kind ) j = jj ;
+		const int slot = j*32+int( lane ) ;
+		int nk = kind ;
+		switch ( kind ) {
+			case K_NODE: {
+				// node steps dominate: stay with them (one ballot per step instead of a full
+				// vote) while enough lanes still have one
+				int jn = j ;
+				while ( true ) {
+					if ( jn>=0 ) {
+						const int kn = step_node( p, jn*32+int( lane ), a.S ) ;
+#pragma unroll
+						for ( int jj = 0 ; jj<RTX_K ; jj++ ) if ( jj == jn ) kinds[jj] = kn ;
+					}
+					jn = -1 ;
+#pragma unroll
+					for ( int jj = RTX_K-1 ; jj>=0 ; jj-- ) if ( kinds[jj] == K_NODE ) jn = jj ;
+					if ( __popc( __ballot_sync( 0xffffffffu, jn>=0 ) )<RTX_STICKY )
+						break ;
+				}
+				j = -1 ;   // kinds[] already updated
 				break ;
-			int j = -1 ;
-#pragma unroll
-			for ( int jj = RTX_K-1 ; jj>=0 ; jj-- ) if ( kinds[jj] == kind ) j = jj ;
-			const int slot = j*32+int( lane ) ;
-			int nk = kind ;
-			switch ( kind ) {
-				case K_NODE: {
-					// node steps dominate: stay with them (one ballot per step instead of a full
-					// vote) while enough lanes still have one
-					int jn = j ;
-					while ( true ) {
-						if ( jn>=0 ) {
-							const int kn = step_node( p, jn*32+int( lane ), a.S ) ;
-#pragma unroll
-							for ( int jj = 0 ; jj<RTX_K ; jj++ ) if ( jj == jn ) kinds[jj] = kn ;
-						}
-						jn = -1 ;
-#pragma unroll
-						for ( int jj = RTX_K-1 ; jj>=0 ; jj-- ) if ( kinds[jj] == K_NODE ) jn = jj ;
-						if ( __popc( __ballot_sync( 0xffffffffu, jn>=0 ) )<RTX_STICKY )
-							break ;
+			}
+			case K_LEAF:
+				if ( j>=0 ) nk = step_leaf( p, slot, a.S ) ;
+				break ;
+			case K_THING:
+				if ( j>=0 ) nk = step_thing( p, slot, a.S ) ;
+				break ;
+			case K_SHADE:
+				if ( j>=0 ) {
+					f3 c, gn, ga ; bool g ;
+					uint32_t segments ;
+					nk = step_shade( p, slot, a.S, c, g, gn, ga, segments ) ;
+					const size_t pix = size_t( uint32_t( p.i( F_PIX, slot ) ) ) ;
+					if ( GUIDES && g ) {
+						const float v[6] = { gn.x, gn.y, gn.z, ga.x, ga.y, ga.z } ;
+						for ( int q = 0 ; q<6 ; q++ )
+							atomicAdd( guide+6*pix+q, ( unsigned long long )( long long )( v[q]*1073741824.f ) ) ;
 					}
-					j = -1 ;   // kinds[] already updated
-					break ;
+					if ( nk == K_REGEN ) {
+						// (0 contributions -- absorbed paths -- need no atomic)
+						const unsigned long long r = tofix( c.x ), gg = tofix( c.y ), bb = tofix( c.z ) ;
+						if ( r )  atomicAdd( accum+4*pix, r ) ;
+						if ( gg ) atomicAdd( accum+4*pix+1, gg ) ;
+						if ( bb ) atomicAdd( accum+4*pix+2, bb ) ;
+						atomicAdd( accum+4*pix+3, ( unsigned long long ) segments ) ;
+					}
 				}
-				case K_LEAF:
-					if ( j>=0 ) nk = step_leaf( p, slot, a.S ) ;
-					break ;
-				case K_THING:
-					if ( j>=0 ) nk = step_thing( p, slot, a.S ) ;
-					break ;
-				case K_SHADE:
-					if ( j>=0 ) {
-						f3 c, gn, ga ; bool g ;
-						nk = step_shade( p, slot, a.S, c, g, gn, ga ) ;
-						const uint32_t px = uint32_t( p.i( F_PIX, slot ) ) ;
-						atomicAdd( segs+px, 1u ) ;
-						if ( GUIDES && g ) {
-							const float v[6] = { gn.x, gn.y, gn.z, ga.x, ga.y, ga.z } ;
-							for ( int q = 0 ; q<6 ; q++ )
-								atomicAdd( gacc+32*q+px, ( unsigned long long )( long long )( v[q]*1073741824.f ) ) ;
-						}
-						if ( nk == K_REGEN ) {
-							atomicAdd( acc+px, ( unsigned long long ) tofix( c.x ) ) ;
-							atomicAdd( acc+32+px, ( unsigned long long ) tofix( c.y ) ) ;
-							atomicAdd( acc+64+px, ( unsigned long long ) tofix( c.z ) ) ;
+				break ;
+			default: {   // K_REGEN: hand the next paths of the warp's unit(s) to the lanes that ask
+				uint32_t want = __ballot_sync( 0xffffffffu, j>=0 ) ;
+				while ( want ) {
+					if ( unit_left == 0 && ! exhausted ) {
+						uint32_t u = 0 ;
+						if ( lane == 0 ) u = atomicAdd( unit_counter, 1u ) ;
+						u = __shfl_sync( 0xffffffffu, u, 0 ) ;
+						if ( u>=n_units )
+							exhausted = true ;
+						else {
+							const uint32_t tile = u%n_tiles, chunk = u/n_tiles ;
+							unit_x0 = ( tile%tiles_x )*8u ; unit_y0 = ( tile/tiles_x )*4u ;
+							unit_s0 = chunk*RTX_UNIT_SPP ;
+							unit_pos = 0 ;
+							unit_left = 32u*min( RTX_UNIT_SPP, a.spp-unit_s0 ) ;
 						}
 					}
-					break ;
-				default: {   // K_REGEN
-					const uint32_t want = __ballot_sync( 0xffffffffu, j>=0 ) ;
-					const uint32_t idx = next+__popc( want&lt ) ;
-					next += __popc( want ) ;
-					if ( j>=0 ) {
-						if ( idx<total ) {
-							// path idx -> (sample, pixel of the tile); tiles cut by the image border take the slow way
-							uint32_t px, smp ;
-							if ( n_valid == 32u ) { px = idx&31u ; smp = idx>>5 ; }
-							else { px = __fns( vmask, 0, int( idx%n_valid )+1 ) ; smp = idx/n_valid ; }
-							nk = step_regen( p, slot, a.S, a.cam, x0+( px&7u ), y0+( px>>3 ), a.w, a.h, px, a.seed, a.sample0+smp*a.sample_stride, a.depth ) ;
-						} else
-							nk = K_DONE ;
+					if ( exhausted ) {
+						if ( ( want>>lane )&1u ) nk = K_DONE ;
+						break ;
 					}
+					const uint32_t take = min( uint32_t( __popc( want ) ), unit_left ) ;
+					const uint32_t rank = __popc( want&lt ) ;
+					const bool served = ( ( want>>lane )&1u ) && rank<take ;
+					if ( served ) {
+						// path idx of the unit -> (sample, pixel of the tile); pixels beyond the image
+						// border are skipped (the lane asks again)
+						const uint32_t idx = unit_pos+rank ;
+						const uint32_t px = idx&31u, smp = unit_s0+( idx>>5 ) ;
+						const uint32_t x = unit_x0+( px&7u ), y = unit_y0+( px>>3 ) ;
+						if ( x<a.w && y<a.h )
+							nk = step_regen( p, slot, a.S, a.cam, x, y, a.w, a.h, a.w*y+x, a.seed, a.sample0+smp*a.sample_stride, a.depth ) ;
+					}
+					unit_pos += take ; unit_left -= take ;
+					want &= ~__ballot_sync( 0xffffffffu, served ) ;
 				}
 			}
+		}
 #pragma unroll
-			for ( int jj = 0 ; jj<RTX_K ; jj++ ) if ( jj == j ) kinds[jj] = nk ;
-		}
-		__syncwarp() ;
-
-		if ( ( vmask>>lane )&1u ) {
-			const uint32_t pix = a.w*( y0+( lane>>3 ) )+x0+( lane&7u ) ;
-			ulonglong2* out = reinterpret_cast<ulonglong2*>( a.accum+4*size_t( pix ) ) ;
-			ulonglong2 lo = make_ulonglong2( acc[lane], acc[32+lane] ), hi = make_ulonglong2( acc[64+lane], ( unsigned long long ) segs[lane] ) ;
-			if ( a.accumulate ) {
-				const ulonglong2 plo = out[0], phi = out[1] ;
-				lo.x += plo.x ; lo.y += plo.y ; hi.x += phi.x ; hi.y += phi.y ;
-			}
-			out[0] = lo ; out[1] = hi ;
-			if ( GUIDES )
-				for ( int g = 0 ; g<6 ; g++ ) {
-					long long* o = a.guide_acc+6*size_t( pix )+g ;
-					*o = ( a.accumulate ? *o : 0ll )+( long long ) gacc[32*g+lane] ;
-				}
-		}
-		__syncwarp() ;
+		for ( int jj = 0 ; jj<RTX_K ; jj++ ) if ( jj == j ) kinds[jj] = nk ;
 	}
 }
 

@@ -43,7 +43,7 @@ enum {
 	F_T, F_THING, F_PRIM, F_U, F_V,                          // best hit so far
 	F_CUR, F_LEVEL, F_SP,                                    // next work item; thing being traversed (-1: top); stack size
 	F_NODES0, F_NODES1, F_TRIS0, F_TRIS1,                    // node / triangle arrays of the current level
-	F_THRX, F_THRY, F_THRZ, F_RNG0, F_RNG1, F_PIX, F_META,   // path: throughput, stream, tile pixel, sample<<8|depth left
+	F_THRX, F_THRY, F_THRZ, F_RNG0, F_RNG1, F_PIX, F_META,   // path: throughput, stream, pixel index, counters (see step_shade)
 	F_STACK,
 	F_WORDS = F_STACK+2*RTX_POOL_STACK
 } ;
@@ -306,15 +306,16 @@ template <class P> RTX_HD int step_thing( P& p, int slot, const SceneDev& S ) {
 // Guide layers: the first diffuse or reflecting hit of a path contributes its normal and
 // albedo (optx/optics_i.cu:97-101, 185-189; refracting hits do not); bit 8 of F_META marks
 // a path that has contributed.  `guide` is set when this call captured them.
-template <class P> RTX_HD int step_shade( P& p, int slot, const SceneDev& S, f3& c, bool& guide, f3& gnormal, f3& galbedo ) {
+template <class P> RTX_HD int step_shade( P& p, int slot, const SceneDev& S, f3& c, bool& guide, f3& gnormal, f3& galbedo, uint32_t& segments ) {
 	guide = false ;
 	HitRec h ;
 	RTX_COUNT( rays ) ;
 	h.t = p.f( F_T, slot ) ; h.thing = p.i( F_THING, slot ) ; h.prim = p.i( F_PRIM, slot ) ; h.u = p.f( F_U, slot ) ; h.v = p.f( F_V, slot ) ;
 	const f3 ori = ld3( p, F_OX, slot ), dir = ld3( p, F_DX, slot ) ;
 	f3 thr = ld3( p, F_THRX, slot ) ;
-	const uint32_t meta = uint32_t( p.i( F_META, slot ) ) ;
+	const uint32_t meta = uint32_t( p.i( F_META, slot ) )+512u ;   // bits 0-7 depth left, 8 guide taken, 9-15 segments of the path
 	const uint32_t depth_left = meta&255u ;
+	segments = meta>>9 ;
 	c = mk3( 0.f, 0.f, 0.f ) ;
 	if ( h.thing<0 ) {
 		c = thr*sky( dir ) ;

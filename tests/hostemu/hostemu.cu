@@ -66,7 +66,7 @@ f3 pool_path( const SceneDev& S, const CameraDev& cam, uint32_t x, uint32_t y, u
 			case K_NODE:  kind = step_node( P, 0, S ) ; break ;
 			case K_LEAF:  kind = step_leaf( P, 0, S ) ; break ;
 			case K_THING: kind = step_thing( P, 0, S ) ; break ;
-			case K_SHADE: { segments++ ; bool g ; f3 gn, ga ; kind = step_shade( P, 0, S, c, g, gn, ga ) ; break ; }
+			case K_SHADE: { segments++ ; bool g ; f3 gn, ga ; uint32_t sg ; kind = step_shade( P, 0, S, c, g, gn, ga, sg ) ; break ; }
 			default: return c ;
 		}
 	}
