@@ -75,12 +75,17 @@ inline uint32_t tile_grid( uint32_t w, uint32_t h ) {
 // integer atomics: order free, bit-reproducible, and no per-tile buffers.
 #define RTX_POOL_R ( 32*RTX_K )
 #ifndef RTX_STICKY
-#define RTX_STICKY 14          // keep doing node steps while at least this many lanes have one
+#define RTX_STICKY 5           // keep doing node steps while at least this many lanes have one (swept: 4-6 best)
 #endif
 #ifndef RTX_MIN_CTAS
 #define RTX_MIN_CTAS 20         // resident render warps per SM the register budget is set for (96 registers)
 #endif
+#ifndef RTX_NODE_BIAS
+#define RTX_NODE_BIAS 0         // votes added to the node kind
+#endif
+#ifndef RTX_UNIT_SPP
 #define RTX_UNIT_SPP 16u
+#endif
 template <bool GUIDES>
 __global__ void __launch_bounds__( 32, RTX_MIN_CTAS ) k_render( const FrameArgs a, uint32_t* unit_counter, int32_t* ovf_all ) {
 	const uint32_t lane = threadIdx.x ;
@@ -116,7 +121,7 @@ __global__ void __launch_bounds__( 32, RTX_MIN_CTAS ) k_render( const FrameArgs 
 		// one ray per lane: lanes of equal kind find each other (match), the largest group
 		// wins (warp-wide max of size<<3|kind)
 		const uint32_t peers = __match_any_sync( 0xffffffffu, kinds[0] ) ;
-		const int kind = int( __reduce_max_sync( 0xffffffffu, kinds[0] == K_DONE ? 0u : ( uint32_t( __popc( peers ) )<<3 )|uint32_t( kinds[0] ) )&7u ) ;
+		const int kind = int( __reduce_max_sync( 0xffffffffu, kinds[0] == K_DONE ? 0u : ( uint32_t( __popc( peers )+( kinds[0] == K_NODE ? RTX_NODE_BIAS : 0 ) )<<3 )|uint32_t( kinds[0] ) )&7u ) ;
 #else
 		uint32_t mine = 0 ;
 #pragma unroll
@@ -175,10 +180,14 @@ __global__ void __launch_bounds__( 32, RTX_MIN_CTAS ) k_render( const FrameArgs 
 					if ( nk == K_REGEN ) {
 						// (0 contributions -- absorbed paths -- need no atomic)
 						const unsigned long long r = tofix( c.x ), gg = tofix( c.y ), bb = tofix( c.z ) ;
+#if ! defined( RTX_EXPERIMENT_NO_ACCUM )
 						if ( r )  atomicAdd( accum+4*pix, r ) ;
 						if ( gg ) atomicAdd( accum+4*pix+1, gg ) ;
 						if ( bb ) atomicAdd( accum+4*pix+2, bb ) ;
 						atomicAdd( accum+4*pix+3, ( unsigned long long ) segments ) ;
+#else
+						if ( r+gg+bb == 1 ) atomicAdd( accum+4*pix+3, ( unsigned long long ) segments ) ;
+#endif
 					}
 				}
 				break ;
