@@ -147,7 +147,7 @@ struct q4 { float x, y, z, w ; } ;   // 16-byte record, bit-compatible with floa
 // (count-1); RTX_REF_EMPTY marks an unused slot.  The two values above it are stack
 // sentinels.
 #define RTX_NODE_RECS  8
-#define RTX_TRI_RECS   4            // a triangle: (v0, prim id) (e1,-) (e2,-) (pad) = 64 bytes, two 256-bit loads
+#define RTX_TRI_RECS   4            // a triangle: (a, prim id) (e1, b.x) (e2, b.y) (b.z, c) = 64 bytes, two 256-bit loads
 #define RTX_WIDTH      4
 #define RTX_LEAF_MAX   4            // triangles per mesh leaf (top level: 1 thing per leaf)
 #define RTX_REF_EMPTY  0x7ffffffd
@@ -193,6 +193,7 @@ struct HitRec {
 	int32_t thing ;   // -1: miss
 	int32_t prim ;    // -1: analytic
 	float   u, v ;    // barycentrics (mesh)
+	int32_t slot ;    // triangle record of the hit in the mesh's leaf-ordered array
 } ;
 
 // shading frame of a hit
@@ -348,7 +349,7 @@ RTX_HD float slab( float lox, float loy, float loz, float hix, float hiy, float 
 // RTX_STK_RETURN, popping it restores the world-space ray; RTX_STK_DONE sits at the bottom.
 template <class Stack>
 RTX_HD void closest( const SceneDev& S, const f3& o, const f3& d, float tmin, Stack& st, HitRec& best, bool active = true ) {
-	best.t = INFINITY ; best.thing = -1 ; best.prim = -1 ; best.u = 0.f ; best.v = 0.f ;
+	best.t = INFINITY ; best.thing = -1 ; best.prim = -1 ; best.u = 0.f ; best.v = 0.f ; best.slot = 0 ;
 	if ( S.n_things == 0 )   // uniform over the launch
 		return ;
 	float tbest_s = INFINITY ;
@@ -421,7 +422,7 @@ RTX_HD void closest( const SceneDev& S, const f3& o, const f3& d, float tmin, St
 					if ( tri_test( mk3( a.x, a.y, a.z ), mk3( b.x, b.y, b.z ), mk3( c.x, c.y, c.z ), ohi, olo, dd, tmin, t, u, v ) ) {
 						const int32_t prim = asint( a.w ) ;
 						if ( better( t, thing, prim, best ) ) {
-							best.t = t ; best.thing = thing ; best.prim = prim ; best.u = u ; best.v = v ;
+							best.t = t ; best.thing = thing ; best.prim = prim ; best.u = u ; best.v = v ; best.slot = int32_t( first+k ) ;
 							tbest_s = t*RTX_SLACK ;
 							RTX_EVENT( 'H' ) ;
 						}
@@ -482,7 +483,7 @@ RTX_HD void closest( const SceneDev& S, const f3& o, const f3& d, float tmin, St
 
 // exhaustive scan (validation instrument; same tests, same tie rule, no boxes)
 RTX_HD void closest_brute( const SceneDev& S, const f3& o, const f3& d, float tmin, HitRec& best ) {
-	best.t = INFINITY ; best.thing = -1 ; best.prim = -1 ; best.u = 0.f ; best.v = 0.f ;
+	best.t = INFINITY ; best.thing = -1 ; best.prim = -1 ; best.u = 0.f ; best.v = 0.f ; best.slot = 0 ;
 	for ( uint32_t k = 0 ; k<S.n_things ; k++ ) {
 		const ThingTrav* tt = S.trav+k ;
 		if ( tt->kind == 0 ) {
@@ -502,7 +503,7 @@ RTX_HD void closest_brute( const SceneDev& S, const f3& o, const f3& d, float tm
 				float t, u, v ;
 				if ( tri_test( mk3( a.x, a.y, a.z ), mk3( b.x, b.y, b.z ), mk3( c.x, c.y, c.z ), ohi, olo, dd, tmin, t, u, v ) ) {
 					const int32_t prim = asint( a.w ) ;
-					if ( better( t, int32_t( k ), prim, best ) ) { best.t = t ; best.thing = int32_t( k ) ; best.prim = prim ; best.u = u ; best.v = v ; }
+					if ( better( t, int32_t( k ), prim, best ) ) { best.t = t ; best.thing = int32_t( k ) ; best.prim = prim ; best.u = u ; best.v = v ; best.slot = int32_t( f ) ; }
 				}
 			}
 		}
@@ -529,12 +530,13 @@ RTX_HD_CALL void frame_of( const SceneDev& S, const HitRec& h, const f3& o, cons
 		fr.normal = narrow( fr.facing ? outward : -outward ) ;
 		return ;
 	}
-	const uint32_t* ices = ldptr( &ts->ices ) ;
-	const float*    vces = ldptr( &ts->vces ) ;
-	const uint32_t i0 = RTX_LDG( ices+3*size_t( h.prim ) ), i1 = RTX_LDG( ices+3*size_t( h.prim )+1 ), i2 = RTX_LDG( ices+3*size_t( h.prim )+2 ) ;
-	const d3 a = mk3( double( RTX_LDG( vces+3*size_t( i0 ) ) ), double( RTX_LDG( vces+3*size_t( i0 )+1 ) ), double( RTX_LDG( vces+3*size_t( i0 )+2 ) ) ) ;
-	const d3 b = mk3( double( RTX_LDG( vces+3*size_t( i1 ) ) ), double( RTX_LDG( vces+3*size_t( i1 )+1 ) ), double( RTX_LDG( vces+3*size_t( i1 )+2 ) ) ) ;
-	const d3 c = mk3( double( RTX_LDG( vces+3*size_t( i2 ) ) ), double( RTX_LDG( vces+3*size_t( i2 )+1 ) ), double( RTX_LDG( vces+3*size_t( i2 )+2 ) ) ) ;
+	// the three vertices as uploaded ride in the triangle record the traversal just tested
+	const ThingTrav* tt = S.trav+h.thing ;
+	const q4* T = ldptr( &tt->tris )+size_t( h.slot )*RTX_TRI_RECS ;
+	const q4 t0 = ldq( T ), t1 = ldq( T+1 ), t2 = ldq( T+2 ), t3 = ldq( T+3 ) ;
+	const d3 a = mk3( double( t0.x ), double( t0.y ), double( t0.z ) ) ;
+	const d3 b = mk3( double( t1.w ), double( t2.w ), double( t3.x ) ) ;
+	const d3 c = mk3( double( t3.y ), double( t3.z ), double( t3.w ) ) ;
 	d3 A, B, C ;
 	if ( RTX_LDG( &ts->diag ) ) {
 		A = xfpoint_diag( m[0], m[3], m[5], m[7], m[10], m[11], a ) ;

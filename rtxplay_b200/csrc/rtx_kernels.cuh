@@ -66,6 +66,12 @@ inline uint32_t tile_grid( uint32_t w, uint32_t h ) {
 	return ( warps*32u+RTX_BLOCK-1u )/RTX_BLOCK ;
 }
 
+// fire-and-forget 64-bit add to GLOBAL memory (RED.E.ADD.64): atomicAdd() on a pointer the
+// compiler only knows as generic emits an ATOM plus a shared-memory CAS spin path
+__device__ __forceinline__ void red_add_u64( unsigned long long* addr, unsigned long long v ) {
+	asm volatile( "red.global.add.u64 [%0], %1;" :: "l"( __cvta_generic_to_global( addr ) ), "l"( v ) : "memory" ) ;
+}
+
 // The path tracer (see rtx_pool.cuh): one warp per CTA, persistent.  Work is handed out in
 // small units -- an 8x4 pixel tile x RTX_UNIT_SPP samples = up to 512 paths -- through a
 // global counter; a warp streams from one unit straight into the next (a lane whose path
@@ -175,16 +181,16 @@ __global__ void __launch_bounds__( 32, RTX_MIN_CTAS ) k_render( const FrameArgs 
 					if ( GUIDES && g ) {
 						const float v[6] = { gn.x, gn.y, gn.z, ga.x, ga.y, ga.z } ;
 						for ( int q = 0 ; q<6 ; q++ )
-							atomicAdd( guide+6*pix+q, ( unsigned long long )( long long )( v[q]*1073741824.f ) ) ;
+							red_add_u64( guide+6*pix+q, ( unsigned long long )( long long )( v[q]*1073741824.f ) ) ;
 					}
 					if ( nk == K_REGEN ) {
 						// (0 contributions -- absorbed paths -- need no atomic)
 						const unsigned long long r = tofix( c.x ), gg = tofix( c.y ), bb = tofix( c.z ) ;
 #if ! defined( RTX_EXPERIMENT_NO_ACCUM )
-						if ( r )  atomicAdd( accum+4*pix, r ) ;
-						if ( gg ) atomicAdd( accum+4*pix+1, gg ) ;
-						if ( bb ) atomicAdd( accum+4*pix+2, bb ) ;
-						atomicAdd( accum+4*pix+3, ( unsigned long long ) segments ) ;
+						if ( r )  red_add_u64( accum+4*pix, r ) ;
+						if ( gg ) red_add_u64( accum+4*pix+1, gg ) ;
+						if ( bb ) red_add_u64( accum+4*pix+2, bb ) ;
+						red_add_u64( accum+4*pix+3, ( unsigned long long ) segments ) ;
 #else
 						if ( r+gg+bb == 1 ) atomicAdd( accum+4*pix+3, ( unsigned long long ) segments ) ;
 #endif

@@ -303,7 +303,7 @@ __global__ void __launch_bounds__( 256 ) k_tri_bounds( const float* vces, const 
 	plo[f] = { fminf( a[0], fminf( b[0], c[0] ) ), fminf( a[1], fminf( b[1], c[1] ) ), fminf( a[2], fminf( b[2], c[2] ) ), 0.f } ;
 	phi[f] = { fmaxf( a[0], fmaxf( b[0], c[0] ) ), fmaxf( a[1], fmaxf( b[1], c[1] ) ), fmaxf( a[2], fmaxf( b[2], c[2] ) ), 0.f } ;
 }
-// triangles in leaf order: (v0, prim), e1, e2 -- the edges are float differences (contract)
+// triangles in leaf order: (a, prim) (e1, b.x) (e2, b.y) (b.z, c) -- the edges are float differences (contract)
 __global__ void __launch_bounds__( 256 ) k_pack_tris( const float* vces, const uint32_t* ices, const uint32_t* vals, uint32_t nt, q4* tris ) {
 	const uint32_t j = blockIdx.x*blockDim.x+threadIdx.x ;
 	if ( j>=nt ) return ;
@@ -312,9 +312,9 @@ __global__ void __launch_bounds__( 256 ) k_pack_tris( const float* vces, const u
 	const float* a = vces+3*size_t( i0 ) ; const float* b = vces+3*size_t( i1 ) ; const float* c = vces+3*size_t( i2 ) ;
 	q4* T = tris+size_t( j )*RTX_TRI_RECS ;
 	T[0] = { a[0], a[1], a[2], __int_as_float( int( f ) ) } ;
-	T[1] = { b[0]-a[0], b[1]-a[1], b[2]-a[2], 0.f } ;
-	T[2] = { c[0]-a[0], c[1]-a[1], c[2]-a[2], 0.f } ;
-	T[3] = { 0.f, 0.f, 0.f, 0.f } ;
+	T[1] = { b[0]-a[0], b[1]-a[1], b[2]-a[2], b[0] } ;
+	T[2] = { c[0]-a[0], c[1]-a[1], c[2]-a[2], b[1] } ;
+	T[3] = { b[2], c[0], c[1], c[2] } ;   // the vertices as uploaded, for the shading frame
 }
 // world bounds of every thing: analytic sphere c +- r; mesh = its root box corners mapped
 // through the double transform.  root boxes are [lo,hi] of each thing's mesh.

@@ -40,7 +40,7 @@ enum {
 	F_OX, F_OY, F_OZ, F_DX, F_DY, F_DZ,                      // world ray
 	F_HX, F_HY, F_HZ, F_LX, F_LY, F_LZ, F_EX, F_EY, F_EZ,    // object ray: origin hi, lo; direction
 	F_IX, F_IY, F_IZ, F_QX, F_QY, F_QZ,                      // current level: 1/d, o/d
-	F_T, F_THING, F_PRIM, F_U, F_V,                          // best hit so far
+	F_T, F_THING, F_PRIM, F_U, F_V, F_TRIJ,                  // best hit so far (F_TRIJ: its triangle record)
 	F_CUR, F_LEVEL, F_SP,                                    // next work item; thing being traversed (-1: top); stack size
 	F_NODES0, F_NODES1, F_TRIS0, F_TRIS1,                    // node / triangle arrays of the current level
 	F_THRX, F_THRY, F_THRZ, F_RNG0, F_RNG1, F_PIX, F_META,   // path: throughput, stream, pixel index, counters (see step_shade)
@@ -223,7 +223,7 @@ template <class P> RTX_HD int step_leaf( P& p, int slot, const SceneDev& S ) {
 	const uint32_t first = ref>>3, count = ( ref&7u )+1u ;
 	const f3 ohi = ld3( p, F_HX, slot ), olo = ld3( p, F_LX, slot ), dd = ld3( p, F_EX, slot ) ;
 	HitRec best ;
-	best.t = p.f( F_T, slot ) ; best.thing = p.i( F_THING, slot ) ; best.prim = p.i( F_PRIM, slot ) ; best.u = 0.f ; best.v = 0.f ;
+	best.t = p.f( F_T, slot ) ; best.thing = p.i( F_THING, slot ) ; best.prim = p.i( F_PRIM, slot ) ; best.u = 0.f ; best.v = 0.f ; best.slot = 0 ;
 	const q4* tris = ldp<P, q4>( p, F_TRIS0, slot ) ;
 	bool changed = false ;
 	RTX_COUNT( leaves ) ;
@@ -236,14 +236,14 @@ template <class P> RTX_HD int step_leaf( P& p, int slot, const SceneDev& S ) {
 		if ( tri_test( mk3( a.x, a.y, a.z ), mk3( b.x, b.y, b.z ), mk3( c.x, c.y, c.z ), ohi, olo, dd, 1e-3f, t, u, v ) ) {
 			const int32_t prim = asint( a.w ) ;
 			if ( better( t, level, prim, best ) ) {
-				best.t = t ; best.thing = level ; best.prim = prim ; best.u = u ; best.v = v ;
+				best.t = t ; best.thing = level ; best.prim = prim ; best.u = u ; best.v = v ; best.slot = int32_t( first+k ) ;
 				changed = true ;
 			}
 		}
 	}
 	if ( changed ) {
 		p.sf( F_T, slot, best.t ) ; p.si( F_THING, slot, best.thing ) ; p.si( F_PRIM, slot, best.prim ) ;
-		p.sf( F_U, slot, best.u ) ; p.sf( F_V, slot, best.v ) ;
+		p.sf( F_U, slot, best.u ) ; p.sf( F_V, slot, best.v ) ; p.si( F_TRIJ, slot, best.slot ) ;
 	}
 	cur = pop_next( p, slot, S, sp, level ) ;
 	return finish_step( p, slot, cur, sp, level ) ;
@@ -310,7 +310,7 @@ template <class P> RTX_HD int step_shade( P& p, int slot, const SceneDev& S, f3&
 	guide = false ;
 	HitRec h ;
 	RTX_COUNT( rays ) ;
-	h.t = p.f( F_T, slot ) ; h.thing = p.i( F_THING, slot ) ; h.prim = p.i( F_PRIM, slot ) ; h.u = p.f( F_U, slot ) ; h.v = p.f( F_V, slot ) ;
+	h.t = p.f( F_T, slot ) ; h.thing = p.i( F_THING, slot ) ; h.prim = p.i( F_PRIM, slot ) ; h.u = p.f( F_U, slot ) ; h.v = p.f( F_V, slot ) ; h.slot = p.i( F_TRIJ, slot ) ;
 	const f3 ori = ld3( p, F_OX, slot ), dir = ld3( p, F_DX, slot ) ;
 	f3 thr = ld3( p, F_THRX, slot ) ;
 	const uint32_t meta = uint32_t( p.i( F_META, slot ) )+512u ;   // bits 0-7 depth left, 8 guide taken, 9-15 segments of the path

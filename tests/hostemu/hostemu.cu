@@ -201,8 +201,9 @@ void build_scene( EmuScene& E, const double* things, int n_things, int n_meshes,
 			const uint32_t f = m.tree.order[j] ;
 			const float* a = &m.vces[3*size_t( m.ices[3*f] )] ; const float* b = &m.vces[3*size_t( m.ices[3*f+1] )] ; const float* c = &m.vces[3*size_t( m.ices[3*f+2] )] ;
 			m.tris[RTX_TRI_RECS*size_t( j )]   = { a[0], a[1], a[2], asfloat( int( f ) ) } ;
-			m.tris[RTX_TRI_RECS*size_t( j )+1] = { b[0]-a[0], b[1]-a[1], b[2]-a[2], 0.f } ;
-			m.tris[RTX_TRI_RECS*size_t( j )+2] = { c[0]-a[0], c[1]-a[1], c[2]-a[2], 0.f } ;
+			m.tris[RTX_TRI_RECS*size_t( j )+1] = { b[0]-a[0], b[1]-a[1], b[2]-a[2], b[0] } ;
+			m.tris[RTX_TRI_RECS*size_t( j )+2] = { c[0]-a[0], c[1]-a[1], c[2]-a[2], b[1] } ;
+			m.tris[RTX_TRI_RECS*size_t( j )+3] = { b[2], c[0], c[1], c[2] } ;
 		}
 	}
 	E.trav.resize( n_things ) ; E.shade.resize( n_things ) ; E.bsphere.resize( n_things ) ;
