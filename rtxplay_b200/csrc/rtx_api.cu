@@ -271,7 +271,11 @@ void upload_things( rtx_ctx* c ) {
 			t.kind = 0 ; s.kind = 0 ;
 			t.inv[0] = double( th.xf[3] ) ; t.inv[1] = double( th.xf[7] ) ; t.inv[2] = double( th.xf[11] ) ; t.inv[3] = double( th.xf[0] ) ;
 			lo[k] = { 0, 0, 0, 0 } ; hi[k] = { 0, 0, 0, 0 } ;
-			bs[k] = { 0.f, 0.f, 0.f, -1.f } ;   // the sphere test itself is the test
+			{	// the padded sphere itself: a cheap float pre-test in front of the double-precision roots
+				const double unit[4] = { 0., 0., 0., 1. } ;
+				const float sx[12] = { std::fabs( th.xf[0] ), 0, 0, th.xf[3], 0, std::fabs( th.xf[0] ), 0, th.xf[7], 0, 0, std::fabs( th.xf[0] ), th.xf[11] } ;
+				world_bsphere( sx, unit, &bs[k].x ) ;
+			}
 		} else {
 			world_bsphere( th.xf, m.bsphere, &bs[k].x ) ;
 			t.kind = 1 ; s.kind = 1 ;

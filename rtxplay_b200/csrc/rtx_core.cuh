@@ -144,7 +144,7 @@ struct q4 { float x, y, z, w ; } ;   // 16-byte record, bit-compatible with floa
 //   r3 = hi.x[0..3]  r4 = hi.y[0..3]  r5 = hi.z[0..3]
 //   r6 = child refs[0..3] (bit patterns)   r7 = unused
 // child ref: 0 <= ref < RTX_REF_EMPTY inner node index; ref < 0 leaf, ~ref = first<<3 |
-// (count-1); RTX_REF_EMPTY marks an unused slot.  The two values above it are stack
+// (count-1); RTX_REF_EMPTY marks an unused slot, whose box is lo = hi = +inf (never entered).  The two values above it are stack
 // sentinels.
 #define RTX_NODE_RECS  8
 #define RTX_TRI_RECS   4            // a triangle: (a, prim id) (e1, b.x) (e2, b.y) (b.z, c) = 64 bytes, two 256-bit loads
@@ -380,10 +380,6 @@ RTX_HD void closest( const SceneDev& S, const f3& o, const f3& d, float tmin, St
 				float t1 = slab( lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, idir, ood, tmin, tbest_s ) ;
 				float t2 = slab( lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, idir, ood, tmin, tbest_s ) ;
 				float t3 = slab( lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, idir, ood, tmin, tbest_s ) ;
-				if ( c0 == RTX_REF_EMPTY ) t0 = INFINITY ;
-				if ( c1 == RTX_REF_EMPTY ) t1 = INFINITY ;
-				if ( c2 == RTX_REF_EMPTY ) t2 = INFINITY ;
-				if ( c3 == RTX_REF_EMPTY ) t3 = INFINITY ;
 				// sort the four (entry distance, child) pairs, nearest first
 #define RTX_CSWAP( ta, ca, tb, cb ) if ( tb<ta ) { const float tt = ta ; ta = tb ; tb = tt ; const int32_t cc = ca ; ca = cb ; cb = cc ; }
 				RTX_CSWAP( t0, c0, t1, c1 ) RTX_CSWAP( t2, c2, t3, c3 ) RTX_CSWAP( t0, c0, t2, c2 ) RTX_CSWAP( t1, c1, t3, c3 ) RTX_CSWAP( t1, c1, t2, c2 )

@@ -267,7 +267,7 @@ __global__ void __launch_bounds__( 128 ) k_wide_level( const int2* frontier, uin
 	if ( w>=n_front ) return ;
 	const int2 item = frontier[w] ;
 	float lo[3][RTX_WIDTH], hi[3][RTX_WIDTH] ; int ref[RTX_WIDTH] ;
-	for ( int k = 0 ; k<RTX_WIDTH ; k++ ) { ref[k] = RTX_REF_EMPTY ; for ( int a = 0 ; a<3 ; a++ ) { lo[a][k] = 0.f ; hi[a][k] = 0.f ; } }
+	for ( int k = 0 ; k<RTX_WIDTH ; k++ ) { ref[k] = RTX_REF_EMPTY ; for ( int a = 0 ; a<3 ; a++ ) { lo[a][k] = INFINITY ; hi[a][k] = INFINITY ; } }   // an unused slot: a box no ray enters
 	if ( n == 1 ) {
 		ref[0] = ~0 ;   // the single primitive: slot 0, count 1
 		lo[0][0] = blo[0].x ; lo[1][0] = blo[0].y ; lo[2][0] = blo[0].z ; hi[0][0] = bhi[0].x ; hi[1][0] = bhi[0].y ; hi[2][0] = bhi[0].z ;

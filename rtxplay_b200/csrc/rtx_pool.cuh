@@ -198,10 +198,7 @@ template <class P> RTX_HD int step_node( P& p, int slot, const SceneDev& S ) {
 	float t1 = slab( lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, idir, ood, tmin, tbest_s ) ;
 	float t2 = slab( lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, idir, ood, tmin, tbest_s ) ;
 	float t3 = slab( lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, idir, ood, tmin, tbest_s ) ;
-	if ( c0 == RTX_REF_EMPTY ) t0 = INFINITY ;
-	if ( c1 == RTX_REF_EMPTY ) t1 = INFINITY ;
-	if ( c2 == RTX_REF_EMPTY ) t2 = INFINITY ;
-	if ( c3 == RTX_REF_EMPTY ) t3 = INFINITY ;
+	// (unused child slots hold the box lo = hi = +inf, which no ray enters: no test needed)
 #define RTX_CSWAP( ta, ca, tb, cb ) if ( tb<ta ) { const float tt = ta ; ta = tb ; tb = tt ; const int32_t cc = ca ; ca = cb ; cb = cc ; }
 	RTX_CSWAP( t0, c0, t1, c1 ) RTX_CSWAP( t2, c2, t3, c3 ) RTX_CSWAP( t0, c0, t2, c2 ) RTX_CSWAP( t1, c1, t3, c3 ) RTX_CSWAP( t1, c1, t2, c2 )
 #undef RTX_CSWAP

@@ -139,7 +139,7 @@ void build_tree( const std::vector<q4>& plo, const std::vector<q4>& phi, Tree& T
 		std::vector<I2> next ;
 		for ( const I2& item : front ) {
 			float lo[3][RTX_WIDTH], hi[3][RTX_WIDTH] ; int ref[RTX_WIDTH] ;
-			for ( int k = 0 ; k<RTX_WIDTH ; k++ ) { ref[k] = RTX_REF_EMPTY ; for ( int a = 0 ; a<3 ; a++ ) { lo[a][k] = 0.f ; hi[a][k] = 0.f ; } }
+			for ( int k = 0 ; k<RTX_WIDTH ; k++ ) { ref[k] = RTX_REF_EMPTY ; for ( int a = 0 ; a<3 ; a++ ) { lo[a][k] = INFINITY ; hi[a][k] = INFINITY ; } }
 			if ( n == 1 ) {
 				ref[0] = ~0 ;
 				lo[0][0] = blo[0].x ; lo[1][0] = blo[0].y ; lo[2][0] = blo[0].z ; hi[0][0] = bhi[0].x ; hi[1][0] = bhi[0].y ; hi[2][0] = bhi[0].z ;
@@ -218,7 +218,11 @@ void build_scene( EmuScene& E, const double* things, int n_things, int n_meshes,
 		s.fuzz = float( row[TH_FUZZ] ) ; s.index = float( row[TH_INDEX] ) ; s.type = int( row[TH_TYPE] ) ;
 		if ( int( row[TH_KIND] ) == 0 ) {
 			t.kind = 0 ; s.kind = 0 ;
-			E.bsphere[k] = { 0.f, 0.f, 0.f, -1.f } ;
+			{
+				const double unit[4] = { 0., 0., 0., 1. } ;
+				const float sx[12] = { std::fabs( xf[0] ), 0, 0, xf[3], 0, std::fabs( xf[0] ), 0, xf[7], 0, 0, std::fabs( xf[0] ), xf[11] } ;
+				world_bsphere( sx, unit, &E.bsphere[k].x ) ;
+			}
 			t.inv[0] = double( xf[3] ) ; t.inv[1] = double( xf[7] ) ; t.inv[2] = double( xf[11] ) ; t.inv[3] = double( xf[0] ) ;
 			const double r = fabs( t.inv[3] ) ;
 			plo[k] = { float( t.inv[0]-r )-1e-3f, float( t.inv[1]-r )-1e-3f, float( t.inv[2]-r )-1e-3f, 0.f } ;
