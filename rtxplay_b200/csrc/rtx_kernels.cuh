@@ -99,7 +99,7 @@ __global__ void __launch_bounds__( 32, RTX_MIN_CTAS ) k_render( const FrameArgs 
 #if defined( RTX_REGPOOL )
 	__shared__ uint32_t stack_words[2*RTX_POOL_STACK*32] ;
 	RegPool p ;
-	p.stk = stack_words+lane ;
+	p.stk = uint32_t( __cvta_generic_to_shared( stack_words+lane ) ) ;
 	p.ovf = ovf_all+( size_t( blockIdx.x )*RTX_POOL_R+lane )*RTX_POOL_OVF*2 ;
 #else
 	__shared__ uint32_t words[F_WORDS*RTX_POOL_R] ;
