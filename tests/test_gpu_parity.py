@@ -257,3 +257,36 @@ def test_edge_cases(spheres):
         p.image_w = 64
         ctx.render(p)
     ctx.close()
+
+
+def test_rtwo_cli_batch_output():
+    """The rtwo driver (flow of optx/rtwo.cxx:78-620): PPM image, RPP AOV as PGM, the -S line;
+    rows bottom-up; deterministic; the statistics equal the sum of the AOV."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "rtxplay_b200", "host", "rtwo")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.dirname(exe)], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    runs = []
+    for _ in range(2):
+        r = subprocess.run([exe, "-g", "96x64", "-s", "3", "-d", "50", "-A", "RPP", "-S"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True)
+        runs.append(r)
+    assert runs[0].stdout == runs[1].stdout
+    tok = runs[0].stdout.split()
+    assert tok[:4] == [b"P3", b"96", b"64", b"255"]
+    n = 96 * 64
+    rgb = np.array(tok[4:4 + 3 * n], dtype=np.int64)
+    assert rgb.min() >= 0 and rgb.max() <= 255 and rgb.std() > 10
+    rest = tok[4 + 3 * n:]
+    assert rest[:4] == [b"P2", b"96", b"64", b"65535"]
+    rpp = np.array(rest[4:4 + n], dtype=np.int64)
+    assert rpp.min() >= 3                                    # at least one segment per sample
+    stats = runs[0].stderr.decode().split()
+    assert int(stats[0]) == n and int(stats[1]) == int(rpp.sum())
+    # the top rows of the image are sky: rows are written bottom-up like the reference
+    img = rgb.reshape(64, 96, 3)
+    assert img[0, :, 2].mean() > img[-1, :, 2].mean()
+    # analytic mode and a bad option
+    r = subprocess.run([exe, "--analytic", "-g", "64x48", "-s", "1", "-q", "-S"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True)
+    assert r.stdout == b"" and b"(pixel, rays, milliseconds)" in r.stderr
