@@ -170,6 +170,9 @@ def run_b200(a):
     ctx.resize(a.width, a.height)
     cam = api.camera(aspratio=a.width / a.height)
     st0 = ctx.stats()
+    mesh_stages, top_stages = ctx.build_stages()
+    # L2 read peak of this box: all SMs read a 32 MiB buffer 1000 times past L1
+    l2_peak = ctx.probe_read(32 << 20, 1000) if rank == 0 else None
     n_prims = st0["n_triangles_instanced"] if a.mode == "mesh" else st0["n_things"]
 
     # this rank's share of the frame's samples: global indices rank, rank+world, ...
@@ -269,7 +272,7 @@ def run_b200(a):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(a), "segments_per_frame": segments, "paths_per_frame": a.width * a.height * a.spp,
-                       "build_ms": {"meshes": st["ms_build_blas"], "top_level": st["ms_build_tlas"]}, "device_mb": st["bytes_device"] / 1048576.,
+                       "build_ms": {"meshes": st["ms_build_blas"], "top_level": st["ms_build_tlas"], "mesh_stages": mesh_stages, "top_level_stages": top_stages}, "device_mb": st["bytes_device"] / 1048576.,
                        "things": st["n_things"], "triangles_instanced": st["n_triangles_instanced"], "triangles_stored": st["n_triangles"],
                        "parallelism": "spp split over %d rank(s) + NCCL reduce of the u64 accumulation buffer" % world if world > 1 else "1 GPU",
                        "l2": "256 MiB device write between steps (inside the timed region)",
@@ -278,6 +281,8 @@ def run_b200(a):
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "bytes_per_segment": bytes_seg, "kernel_ms": k_ms,
                          "note": "algorithmic node+primitive bytes of SURVEY.md 8(d); the working set is L1/L2 resident (ncu: 88 MB of DRAM traffic per launch against 2.2 TB of algorithmic bytes), so this is a cache-bandwidth figure quoted against the HBM peak; the kernel is bound by instruction issue and SIMD efficiency (DESIGN.md 4)",
+                         "l2": {"achieved": achieved, "peak": l2_peak, "unit": "GB/s", "frac": achieved / l2_peak if l2_peak else None,
+                                "peak_source": "measured in this run: rtx_probe_read, 32 MiB buffer read 1000x by all SMs with ld.global.cg.v4"},
                          "fp32": {"flop_per_segment": flop_seg, "achieved_tflops": segs_launch * flop_seg / (k_ms * 1e-3) / 1e12,
                                   "peak_tflops": fp32_peak, "frac": segs_launch * flop_seg / (k_ms * 1e-3) / 1e12 / fp32_peak}},
             "e2e": {"value": segments / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": ctypes.sizeof(ctx.params(cam, 1)),

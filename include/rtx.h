@@ -137,6 +137,16 @@ int rtx_write( rtx_ctx* ctx, int buffer, const void* host_src, size_t bytes ) ;
 
 /* the -S line of optx/rtwo.cxx:579-591 and more */
 int rtx_stats_get( rtx_ctx* ctx, rtx_stats* out ) ;
+/* measurement instrument: read bandwidth of a `bytes` buffer read `repeats` times by all SMs,
+ * bypassing L1 -- the L2 read peak when the buffer fits L2 (SURVEY.md 8(d) asks for it measured
+ * on the box), the HBM read peak when it is far larger.  No counterpart in the reference. */
+int rtx_probe_read( rtx_ctx* ctx, size_t bytes, uint32_t repeats, float* gb_per_s ) ;
+/* device time of the stages of the hierarchy builds (stress configuration):
+ * [0] centroid bounds + Morton keys, [1] radix sort, [2] Karras hierarchy, [3] bottom-up
+ * boxes, [4] collapse into wide nodes.  blas_ms: summed over all rtx_mesh_create calls so far;
+ * tlas_ms: the last rtx_accel_build (a refit fills [3] and [4] only).  Either may be NULL.
+ * The reference has no counterpart (optixAccelBuild is opaque, optx/scene.cxx:122, 258). */
+int rtx_build_stages( rtx_ctx* ctx, float blas_ms[5], float tlas_ms[5] ) ;
 /* device time (CUDA events on the launching stream) of the path-tracing kernel of the last
  * rtx_render / rtx_render_accumulate -- the window optx/rtwo.cxx:542-546 times; no device work */
 int rtx_last_render_ms( rtx_ctx* ctx, float* ms ) ;

@@ -195,6 +195,20 @@ class Context:
         self._ck(self._L.rtx_last_render_ms(self._c, ctypes.byref(ms)))
         return ms.value
 
+    def probe_read(self, nbytes, repeats):
+        """GB/s of all SMs reading an nbytes buffer `repeats` times past L1 (L2 peak if it fits L2)."""
+        g = ctypes.c_float()
+        self._ck(self._L.rtx_probe_read(self._c, ctypes.c_size_t(nbytes), ctypes.c_uint32(repeats), ctypes.byref(g)))
+        return g.value
+
+    BUILD_STAGES = ("keys", "sort", "hierarchy", "boxes", "wide_nodes")
+
+    def build_stages(self):
+        """Device ms per hierarchy-build stage: all meshes so far, and the last top-level build."""
+        b, t = (ctypes.c_float * 5)(), (ctypes.c_float * 5)()
+        self._ck(self._L.rtx_build_stages(self._c, b, t))
+        return dict(zip(self.BUILD_STAGES, [float(v) for v in b])), dict(zip(self.BUILD_STAGES, [float(v) for v in t]))
+
     def stats(self):
         s = RtxStats()
         self._ck(self._L.rtx_stats_get(self._c, ctypes.byref(s)))

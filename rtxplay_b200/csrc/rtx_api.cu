@@ -77,6 +77,7 @@ struct rtx_ctx {
 	int          device = 0 ;
 	std::string  err ;
 	cudaStream_t stream = nullptr ;
+	cudaMemPool_t pool = nullptr ;   // build workspace and hierarchies (talloc)
 	cudaEvent_t  ev0 = nullptr, ev1 = nullptr ;
 
 	std::vector<Mesh>      meshes ;
@@ -116,6 +117,9 @@ struct rtx_ctx {
 	uint64_t bytes = 0 ;
 	uint32_t launches = 0 ;
 	float    ms_render = 0.f, ms_blas = 0.f, ms_tlas = 0.f ;
+	cudaEvent_t stage_ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr } ;   // marks between the stages of the last lbvh_build
+	bool     stage_full = false ;                      // ... a full build (all six marks) or a refit (marks 3-5)
+	float    ms_stage_blas[5] = { 0.f, 0.f, 0.f, 0.f, 0.f }, ms_stage_tlas[5] = { 0.f, 0.f, 0.f, 0.f, 0.f } ;   // keys, sort, hierarchy, boxes, wide nodes
 	uint64_t paths = 0 ;
 } ;
 
@@ -132,24 +136,38 @@ template <class T> void dfree( rtx_ctx* c, T*& p, size_t n ) {
 	if ( p ) { cudaFree( p ) ; c->bytes -= ( n ? n : 1 )*sizeof( T ) ; p = nullptr ; }
 }
 
+// build workspace and hierarchy arrays: stream-ordered allocations from the context's own
+// pool (kept, not returned to the driver, between builds) -- a cudaMalloc/cudaFree pair costs
+// more than the kernels of a small build and cudaFree synchronises the device
+template <class T> T* talloc( rtx_ctx* c, size_t n ) {
+	T* p = nullptr ;
+	if ( n == 0 ) n = 1 ;
+	CK( cudaMallocFromPoolAsync( reinterpret_cast<void**>( &p ), n*sizeof( T ), c->pool, c->stream ) ) ;
+	c->bytes += n*sizeof( T ) ;
+	return p ;
+}
+template <class T> void tfree( rtx_ctx* c, T*& p, size_t n ) {
+	if ( p ) { cudaFreeAsync( p, c->stream ) ; c->bytes -= ( n ? n : 1 )*sizeof( T ) ; p = nullptr ; }
+}
+
 void lbvh_free_binary( rtx_ctx* c, Lbvh& b ) {
 	const size_t n = b.n ;
-	dfree( c, b.child, n>1 ? n-1 : 1 ) ;
-	dfree( c, b.range, n>1 ? n-1 : 1 ) ;
-	dfree( c, b.parent_inner, n>1 ? n-1 : 1 ) ;
-	dfree( c, b.parent_leaf, n ) ;
-	dfree( c, b.blo, 2*n ) ;
-	dfree( c, b.bhi, 2*n ) ;
-	dfree( c, b.flags, n>1 ? n-1 : 1 ) ;
-	dfree( c, b.front0, n ) ;
-	dfree( c, b.front1, n ) ;
-	dfree( c, b.counters, 2 ) ;
+	tfree( c, b.child, n>1 ? n-1 : 1 ) ;
+	tfree( c, b.range, n>1 ? n-1 : 1 ) ;
+	tfree( c, b.parent_inner, n>1 ? n-1 : 1 ) ;
+	tfree( c, b.parent_leaf, n ) ;
+	tfree( c, b.blo, 2*n ) ;
+	tfree( c, b.bhi, 2*n ) ;
+	tfree( c, b.flags, n>1 ? n-1 : 1 ) ;
+	tfree( c, b.front0, n ) ;
+	tfree( c, b.front1, n ) ;
+	tfree( c, b.counters, 2 ) ;
 }
 
 void lbvh_free( rtx_ctx* c, Lbvh& b ) {
 	lbvh_free_binary( c, b ) ;
-	dfree( c, b.nodes, size_t( b.cap_nodes )*RTX_NODE_RECS ) ;
-	dfree( c, b.order, b.n ) ;
+	tfree( c, b.nodes, size_t( b.cap_nodes )*RTX_NODE_RECS ) ;
+	tfree( c, b.order, b.n ) ;
 	b.n = 0 ; b.n_nodes = 0 ; b.cap_nodes = 0 ;
 }
 
@@ -157,10 +175,12 @@ void lbvh_free( rtx_ctx* c, Lbvh& b ) {
 // by level (the host reads back the size of each next frontier)
 void lbvh_refit( rtx_ctx* c, Lbvh& b, const q4* plo, const q4* phi, int leaf_max ) {
 	const int n = int( b.n ) ;
+	CK( cudaEventRecord( c->stage_ev[3], c->stream ) ) ;
 	CK( cudaMemsetAsync( b.flags, 0, sizeof( uint32_t )*( n>1 ? n-1 : 1 ), c->stream ) ) ;
 	k_refit<<<( n+255 )/256, 256, 0, c->stream>>>( plo, phi, b.order, n, b.child, b.parent_inner, b.parent_leaf, b.blo, b.bhi, b.flags ) ;
 	c->launches += 1 ;
 	CK( cudaGetLastError() ) ;
+	CK( cudaEventRecord( c->stage_ev[4], c->stream ) ) ;
 	const int2 root = make_int2( 0, 0 ) ;
 	uint32_t counters[2] = { 1u, 0u } ;   // wide node 0 is the root
 	CK( cudaMemcpyAsync( b.front0, &root, sizeof( int2 ), cudaMemcpyHostToDevice, c->stream ) ) ;
@@ -178,6 +198,8 @@ void lbvh_refit( rtx_ctx* c, Lbvh& b, const q4* plo, const q4* phi, int leaf_max
 		std::swap( fin, fout ) ;
 	}
 	b.n_nodes = counters[0] ;
+	CK( cudaEventRecord( c->stage_ev[5], c->stream ) ) ;
+	c->stage_full = false ;
 	CK( cudaMemcpyAsync( &b.root_lo, b.blo, sizeof( q4 ), cudaMemcpyDeviceToHost, c->stream ) ) ;
 	CK( cudaMemcpyAsync( &b.root_hi, b.bhi, sizeof( q4 ), cudaMemcpyDeviceToHost, c->stream ) ) ;
 	CK( cudaStreamSynchronize( c->stream ) ) ;
@@ -191,58 +213,70 @@ void lbvh_build( rtx_ctx* c, Lbvh& b, const q4* plo, const q4* phi, uint32_t n, 
 	// root): there are fewer than n/leaf_max+1 ... n-1 of those; allocate the safe bound,
 	// shrink after the build
 	b.cap_nodes    = n>1 ? n-1 : 1 ;
-	b.nodes        = dalloc<q4>( c, size_t( b.cap_nodes )*RTX_NODE_RECS ) ;
-	b.order        = dalloc<uint32_t>( c, n ) ;
-	b.child        = dalloc<int2>( c, n>1 ? n-1 : 1 ) ;
-	b.range        = dalloc<int2>( c, n>1 ? n-1 : 1 ) ;
-	b.parent_inner = dalloc<int>( c, n>1 ? n-1 : 1 ) ;
-	b.parent_leaf  = dalloc<int>( c, n ) ;
-	b.blo          = dalloc<q4>( c, 2*size_t( n ) ) ;
-	b.bhi          = dalloc<q4>( c, 2*size_t( n ) ) ;
-	b.flags        = dalloc<uint32_t>( c, n>1 ? n-1 : 1 ) ;
-	b.front0       = dalloc<int2>( c, n ) ;
-	b.front1       = dalloc<int2>( c, n ) ;
-	b.counters     = dalloc<uint32_t>( c, 2 ) ;
+	b.nodes        = talloc<q4>( c, size_t( b.cap_nodes )*RTX_NODE_RECS ) ;
+	b.order        = talloc<uint32_t>( c, n ) ;
+	b.child        = talloc<int2>( c, n>1 ? n-1 : 1 ) ;
+	b.range        = talloc<int2>( c, n>1 ? n-1 : 1 ) ;
+	b.parent_inner = talloc<int>( c, n>1 ? n-1 : 1 ) ;
+	b.parent_leaf  = talloc<int>( c, n ) ;
+	b.blo          = talloc<q4>( c, 2*size_t( n ) ) ;
+	b.bhi          = talloc<q4>( c, 2*size_t( n ) ) ;
+	b.flags        = talloc<uint32_t>( c, n>1 ? n-1 : 1 ) ;
+	b.front0       = talloc<int2>( c, n ) ;
+	b.front1       = talloc<int2>( c, n ) ;
+	b.counters     = talloc<uint32_t>( c, 2 ) ;
 
 	const uint32_t nblocks = ( n+RTX_RS_TILE-1 )/RTX_RS_TILE ;
-	int* bounds = dalloc<int>( c, 6 ) ;
-	uint64_t* keys0 = dalloc<uint64_t>( c, n ) ; uint64_t* keys1 = dalloc<uint64_t>( c, n ) ;
-	uint32_t* vals1 = dalloc<uint32_t>( c, n ) ;
-	uint32_t* counts = dalloc<uint32_t>( c, size_t( 256 )*nblocks ) ;
+	int* bounds = talloc<int>( c, 6 ) ;
+	uint64_t* keys0 = talloc<uint64_t>( c, n ) ; uint64_t* keys1 = talloc<uint64_t>( c, n ) ;
+	uint32_t* vals1 = talloc<uint32_t>( c, n ) ;
+	uint32_t* counts = talloc<uint32_t>( c, size_t( 256 )*nblocks ) ;
 
+	CK( cudaEventRecord( c->stage_ev[0], c->stream ) ) ;
 	k_bounds_init<<<1, 32, 0, c->stream>>>( bounds ) ;
 	k_bounds_reduce<<<min( 1184u, ( n+255u )/256u ), 256, 0, c->stream>>>( plo, phi, n, bounds ) ;
 	k_morton<<<( n+255 )/256, 256, 0, c->stream>>>( plo, phi, n, bounds, keys0, b.order ) ;
 	c->launches += 3 ;
+	CK( cudaEventRecord( c->stage_ev[1], c->stream ) ) ;
 	uint64_t* kin = keys0 ; uint64_t* kout = keys1 ;
 	uint32_t* vin = b.order ; uint32_t* vout = vals1 ;
 	for ( int pass = 0 ; pass<8 ; pass++ ) {
 		const int shift = 8*pass ;
-		k_radix_hist<<<nblocks, 32, 0, c->stream>>>( kin, n, shift, counts, nblocks ) ;
+		k_radix_hist<<<nblocks, 32*RTX_RS_WARPS, 0, c->stream>>>( kin, n, shift, counts, nblocks ) ;
 		k_radix_scan<<<1, 1024, 0, c->stream>>>( counts, 256u*nblocks ) ;
-		k_radix_scatter<<<nblocks, 32, 0, c->stream>>>( kin, vin, n, shift, counts, nblocks, kout, vout ) ;
+		k_radix_scatter<<<nblocks, 32*RTX_RS_WARPS, 0, c->stream>>>( kin, vin, n, shift, counts, nblocks, kout, vout ) ;
 		c->launches += 3 ;
 		std::swap( kin, kout ) ; std::swap( vin, vout ) ;
 	}
 	// 8 passes: the sorted data is back in keys0 / b.order
+	CK( cudaEventRecord( c->stage_ev[2], c->stream ) ) ;
 	if ( n>1 ) {
 		k_karras<<<( n-1+255 )/256, 256, 0, c->stream>>>( keys0, int( n ), b.child, b.range, b.parent_inner, b.parent_leaf ) ;
 		c->launches += 1 ;
 	}
 	CK( cudaGetLastError() ) ;
 	lbvh_refit( c, b, plo, phi, leaf_max ) ;
+	c->stage_full = true ;
 
-	dfree( c, bounds, 6 ) ; dfree( c, keys0, n ) ; dfree( c, keys1, n ) ; dfree( c, vals1, n ) ; dfree( c, counts, size_t( 256 )*nblocks ) ;
+	tfree( c, bounds, 6 ) ; tfree( c, keys0, n ) ; tfree( c, keys1, n ) ; tfree( c, vals1, n ) ; tfree( c, counts, size_t( 256 )*nblocks ) ;
 	if ( ! keep_binary ) {
 		// a mesh is never refitted: drop the binary tree and trim the node array
 		lbvh_free_binary( c, b ) ;
 		if ( b.n_nodes<b.cap_nodes ) {
-			q4* trimmed = dalloc<q4>( c, size_t( b.n_nodes )*RTX_NODE_RECS ) ;
+			q4* trimmed = talloc<q4>( c, size_t( b.n_nodes )*RTX_NODE_RECS ) ;
 			CK( cudaMemcpyAsync( trimmed, b.nodes, sizeof( q4 )*size_t( b.n_nodes )*RTX_NODE_RECS, cudaMemcpyDeviceToDevice, c->stream ) ) ;
-			CK( cudaStreamSynchronize( c->stream ) ) ;
-			dfree( c, b.nodes, size_t( b.cap_nodes )*RTX_NODE_RECS ) ;
+			tfree( c, b.nodes, size_t( b.cap_nodes )*RTX_NODE_RECS ) ;
 			b.nodes = trimmed ; b.cap_nodes = b.n_nodes ;
 		}
+	}
+}
+
+// stage times of the last lbvh_build / lbvh_refit (call after the stream is synchronised)
+void stage_collect( rtx_ctx* c, float* dst, bool add ) {
+	for ( int k = 0 ; k<5 ; k++ ) {
+		float ms = 0.f ;
+		if ( c->stage_full || k>=3 ) CK( cudaEventElapsedTime( &ms, c->stage_ev[k], c->stage_ev[k+1] ) ) ;
+		dst[k] = add ? dst[k]+ms : ms ;
 	}
 }
 
@@ -426,6 +460,22 @@ int rtx_init( int device, rtx_ctx** out ) {
 		c->device = device ;
 		CK( cudaStreamCreateWithFlags( &c->stream, cudaStreamNonBlocking ) ) ;
 		CK( cudaEventCreate( &c->ev0 ) ) ; CK( cudaEventCreate( &c->ev1 ) ) ;
+		for ( cudaEvent_t& e : c->stage_ev ) CK( cudaEventCreate( &e ) ) ;
+		{
+			cudaMemPoolProps pp ;
+			memset( &pp, 0, sizeof( pp ) ) ;
+			pp.allocType = cudaMemAllocationTypePinned ;
+			pp.location.type = cudaMemLocationTypeDevice ; pp.location.id = device ;
+			CK( cudaMemPoolCreate( &c->pool, &pp ) ) ;
+			uint64_t keep = ~0ull ;
+			CK( cudaMemPoolSetAttribute( c->pool, cudaMemPoolAttrReleaseThreshold, &keep ) ) ;
+			// reserve the workspace of a 1 M-triangle build now: growing the pool maps new device
+			// memory, which costs more than the build itself
+			void* warm = nullptr ;
+			CK( cudaMallocFromPoolAsync( &warm, size_t( 256 )<<20, c->pool, c->stream ) ) ;
+			CK( cudaFreeAsync( warm, c->stream ) ) ;
+			CK( cudaStreamSynchronize( c->stream ) ) ;
+		}
 		c->d_pick = dalloc<uint32_t>( c, 1 ) ;
 		c->d_counter = dalloc<unsigned long long>( c, 1 ) ;
 		c->d_tile_counter = dalloc<uint32_t>( c, 1 ) ;
@@ -478,6 +528,9 @@ void rtx_shutdown( rtx_ctx* c ) {
 	dfree( c, c->d_pick, 1 ) ; dfree( c, c->d_counter, 1 ) ; dfree( c, c->d_tile_counter, 1 ) ;
 	dfree( c, c->d_ovf, size_t( c->render_grid )*RTX_POOL_R*RTX_POOL_OVF*2 ) ;
 	cudaEventDestroy( c->ev0 ) ; cudaEventDestroy( c->ev1 ) ;
+	for ( cudaEvent_t e : c->stage_ev ) if ( e ) cudaEventDestroy( e ) ;
+	cudaStreamSynchronize( c->stream ) ;   // the stream-ordered frees above
+	if ( c->pool ) cudaMemPoolDestroy( c->pool ) ;
 	cudaStreamDestroy( c->stream ) ;
 	delete c ;
 }
@@ -497,7 +550,7 @@ int rtx_mesh_create( rtx_ctx* c, const float* xyz, uint32_t nv, const uint32_t* 
 	m.vces = dalloc<float>( c, 3*size_t( nv ) ) ; m.ices = dalloc<uint32_t>( c, 3*size_t( nt ) ) ; m.tris = dalloc<q4>( c, RTX_TRI_RECS*size_t( nt ) ) ;
 	CK( cudaMemcpyAsync( m.vces, xyz, sizeof( float )*3*nv, cudaMemcpyHostToDevice, c->stream ) ) ;
 	CK( cudaMemcpyAsync( m.ices, idx, sizeof( uint32_t )*3*size_t( nt ), cudaMemcpyHostToDevice, c->stream ) ) ;
-	q4* plo = dalloc<q4>( c, nt ) ; q4* phi = dalloc<q4>( c, nt ) ;
+	q4* plo = talloc<q4>( c, nt ) ; q4* phi = talloc<q4>( c, nt ) ;
 	CK( cudaEventRecord( c->ev0, c->stream ) ) ;
 	k_tri_bounds<<<( nt+255 )/256, 256, 0, c->stream>>>( m.vces, m.ices, nt, plo, phi ) ;
 	c->launches += 1 ;
@@ -510,7 +563,8 @@ int rtx_mesh_create( rtx_ctx* c, const float* xyz, uint32_t nv, const uint32_t* 
 	float ms = 0.f ;
 	CK( cudaEventElapsedTime( &ms, c->ev0, c->ev1 ) ) ;
 	c->ms_blas += ms ;
-	dfree( c, plo, nt ) ; dfree( c, phi, nt ) ;
+	stage_collect( c, c->ms_stage_blas, true ) ;
+	tfree( c, plo, nt ) ; tfree( c, phi, nt ) ;
 	*mesh_id = uint32_t( c->meshes.size() ) ;
 	c->meshes.push_back( m ) ;
 	RTX_END( c )
@@ -571,6 +625,7 @@ int rtx_accel_build( rtx_ctx* c ) {
 	CK( cudaEventRecord( c->ev1, c->stream ) ) ;
 	CK( cudaStreamSynchronize( c->stream ) ) ;
 	CK( cudaEventElapsedTime( &c->ms_tlas, c->ev0, c->ev1 ) ) ;
+	if ( n ) stage_collect( c, c->ms_stage_tlas, false ) ;
 	c->built = true ;
 	RTX_END( c )
 }
@@ -586,6 +641,7 @@ int rtx_accel_refit( rtx_ctx* c ) {
 	CK( cudaEventRecord( c->ev1, c->stream ) ) ;
 	CK( cudaStreamSynchronize( c->stream ) ) ;
 	CK( cudaEventElapsedTime( &c->ms_tlas, c->ev0, c->ev1 ) ) ;
+	if ( c->tlas.n ) stage_collect( c, c->ms_stage_tlas, false ) ;
 	RTX_END( c )
 }
 
@@ -751,6 +807,37 @@ int rtx_stats_get( rtx_ctx* c, rtx_stats* out ) {
 	for ( const Mesh& m : c->meshes ) out->n_triangles += m.nt ;
 	for ( const ThingHost& t : c->things ) out->n_triangles_instanced += c->meshes[t.mesh].nt ;
 	out->bytes_device = c->bytes ;
+	RTX_END( c )
+}
+
+int rtx_probe_read( rtx_ctx* c, size_t bytes, uint32_t repeats, float* gb_per_s ) {
+	RTX_TRY( c )
+	CK( cudaSetDevice( c->device ) ) ;
+	if ( bytes<4096 || repeats == 0 || ! gb_per_s ) throw std::runtime_error( "rtx_probe_read: bad arguments" ) ;
+	const size_t n_vec = bytes/16 ;
+	uint4* buf = talloc<uint4>( c, n_vec ) ;
+	CK( cudaMemsetAsync( buf, 0x5a, n_vec*16, c->stream ) ) ;
+	int sms = 0 ;
+	CK( cudaDeviceGetAttribute( &sms, cudaDevAttrMultiProcessorCount, c->device ) ) ;
+	const uint32_t grid = uint32_t( sms )*8u ;
+	k_probe_read<<<grid, 256, 0, c->stream>>>( buf, n_vec, 1u, c->d_tile_counter ) ;   // warm the cache
+	CK( cudaEventRecord( c->ev0, c->stream ) ) ;
+	k_probe_read<<<grid, 256, 0, c->stream>>>( buf, n_vec, repeats, c->d_tile_counter ) ;
+	CK( cudaEventRecord( c->ev1, c->stream ) ) ;
+	c->launches += 2 ;
+	CK( cudaGetLastError() ) ;
+	CK( cudaStreamSynchronize( c->stream ) ) ;
+	float ms = 0.f ;
+	CK( cudaEventElapsedTime( &ms, c->ev0, c->ev1 ) ) ;
+	tfree( c, buf, n_vec ) ;
+	*gb_per_s = float( double( n_vec )*16.*double( repeats )/( double( ms )*1e-3 )/1e9 ) ;
+	RTX_END( c )
+}
+
+int rtx_build_stages( rtx_ctx* c, float blas_ms[5], float tlas_ms[5] ) {
+	RTX_TRY( c )
+	if ( blas_ms ) memcpy( blas_ms, c->ms_stage_blas, sizeof( c->ms_stage_blas ) ) ;
+	if ( tlas_ms ) memcpy( tlas_ms, c->ms_stage_tlas, sizeof( c->ms_stage_tlas ) ) ;
 	RTX_END( c )
 }
 

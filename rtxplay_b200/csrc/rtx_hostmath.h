@@ -57,12 +57,17 @@ inline void world_bsphere( const float xf[12], const double bs[4], float out[4] 
 	double g[9] ;
 	for ( int i = 0 ; i<3 ; i++ ) for ( int j = 0 ; j<3 ; j++ ) g[3*i+j] = m[i]*m[j]+m[3+i]*m[3+j]+m[6+i]*m[6+j] ;
 	double v[3] = { 1., .7, .4 }, lam = 0. ;
-	for ( int it = 0 ; it<64 ; it++ ) {
-		const double w[3] = { g[0]*v[0]+g[1]*v[1]+g[2]*v[2], g[3]*v[0]+g[4]*v[1]+g[5]*v[2], g[6]*v[0]+g[7]*v[1]+g[8]*v[2] } ;
-		lam = std::sqrt( w[0]*w[0]+w[1]*w[1]+w[2]*w[2] ) ;
-		if ( lam == 0. ) break ;
-		v[0] = w[0]/lam ; v[1] = w[1]/lam ; v[2] = w[2]/lam ;
-	}
+	if ( g[1] == 0. && g[2] == 0. && g[5] == 0. )
+		lam = std::max( g[0], std::max( g[4], g[8] ) ) ;   // orthogonal columns (scale + translation, the usual case): exact
+	else
+		for ( int it = 0 ; it<64 ; it++ ) {
+			const double w[3] = { g[0]*v[0]+g[1]*v[1]+g[2]*v[2], g[3]*v[0]+g[4]*v[1]+g[5]*v[2], g[6]*v[0]+g[7]*v[1]+g[8]*v[2] } ;
+			const double was = lam ;
+			lam = std::sqrt( w[0]*w[0]+w[1]*w[1]+w[2]*w[2] ) ;
+			if ( lam == 0. ) break ;
+			v[0] = w[0]/lam ; v[1] = w[1]/lam ; v[2] = w[2]/lam ;
+			if ( it>=4 && std::fabs( lam-was )<=1e-9*lam ) break ;   // (the 1.0001 below covers far more)
+		}
 	// power iteration approaches the largest eigenvalue from below: bound it by the trace too
 	const double sig = std::sqrt( std::min( std::max( lam*1.0001, 0. ), g[0]+g[4]+g[8] ) ) ;
 	const double c[3] = { bs[0]*xf[0]+bs[1]*xf[1]+bs[2]*xf[2]+xf[3], bs[0]*xf[4]+bs[1]*xf[5]+bs[2]*xf[6]+xf[7], bs[0]*xf[8]+bs[1]*xf[9]+bs[2]*xf[10]+xf[11] } ;

@@ -335,4 +335,20 @@ __global__ void __launch_bounds__( 256 ) k_postproc( const float* raw, uchar4* d
 	dst[p] = make_uchar4( static_cast<unsigned char>( c[0]*255 ), static_cast<unsigned char>( c[1]*255 ), static_cast<unsigned char>( c[2]*255 ), 255u ) ;
 }
 
+// Measurement instrument (bench.py): every CTA reads the whole buffer `repeats`
+// times with 128-bit loads that bypass L1 (ld.global.cg) -- with a buffer that fits L2 this is
+// the L2 read bandwidth the node fetches of k_render compete for.
+__global__ void __launch_bounds__( 256 ) k_probe_read( const uint4* buf, size_t n_vec, uint32_t repeats, uint32_t* sink ) {
+	uint32_t acc = 0 ;
+	const size_t stride = size_t( gridDim.x )*blockDim.x ;
+	for ( uint32_t r = 0 ; r<repeats ; r++ )
+#pragma unroll 8
+		for ( size_t i = size_t( blockIdx.x )*blockDim.x+threadIdx.x ; i<n_vec ; i += stride ) {
+			uint4 v ;
+			asm volatile( "ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"( v.x ), "=r"( v.y ), "=r"( v.z ), "=r"( v.w ) : "l"( buf+i ) ) ;
+			acc ^= v.x^v.y^v.z^v.w ;
+		}
+	if ( acc == 0x9e3779b9u ) *sink = acc ;   // (keeps the loads alive)
+}
+
 } // namespace rtx

@@ -159,19 +159,35 @@ __global__ void __launch_bounds__( 256 ) k_morton( const q4* plo, const q4* phi,
 }
 
 // ---- radix sort ----------------------------------------------------------------------
-#define RTX_RS_TILE 2048   // keys per warp
+// Stable LSD radix sort, 8-bit digits.  A CTA of RTX_RS_WARPS warps owns a tile of
+// RTX_RS_TILE consecutive keys; warp w owns the w-th run of RTX_RS_TILE/RTX_RS_WARPS of them
+// and keeps them in registers (all loads of a tile are in flight at once).  k_radix_hist
+// counts digits per tile, k_radix_scan turns the digit-major count table into global
+// offsets, k_radix_scatter re-counts per warp, offsets each warp behind the warps before it
+// and ranks the keys of a 32-key round with __match_any_sync (stable: rounds in order, lanes
+// in order).
+#define RTX_RS_TILE   2048   // keys per CTA
+#define RTX_RS_WARPS  4
+#define RTX_RS_ROUNDS ( RTX_RS_TILE/RTX_RS_WARPS/32 )   // 32-key rounds per warp
 
-__global__ void __launch_bounds__( 32 ) k_radix_hist( const uint64_t* keys, uint32_t n, int shift, uint32_t* counts, uint32_t nblocks ) {
+__global__ void __launch_bounds__( 32*RTX_RS_WARPS ) k_radix_hist( const uint64_t* keys, uint32_t n, int shift, uint32_t* counts, uint32_t nblocks ) {
 	__shared__ uint32_t hist[256] ;
-	for ( int d = threadIdx.x ; d<256 ; d += 32 ) hist[d] = 0 ;
-	__syncwarp() ;
+	for ( int d = threadIdx.x ; d<256 ; d += 32*RTX_RS_WARPS ) hist[d] = 0 ;
+	__syncthreads() ;
 	const uint32_t base = blockIdx.x*RTX_RS_TILE ;
-	for ( uint32_t k = threadIdx.x ; k<RTX_RS_TILE ; k += 32 ) {
-		const uint32_t i = base+k ;
-		if ( i<n ) atomicAdd( hist+uint32_t( ( keys[i]>>shift )&255u ), 1u ) ;
+	uint64_t key[RTX_RS_TILE/( 32*RTX_RS_WARPS )] ;
+#pragma unroll
+	for ( int r = 0 ; r<RTX_RS_TILE/( 32*RTX_RS_WARPS ) ; r++ ) {
+		const uint32_t i = base+uint32_t( r )*32u*RTX_RS_WARPS+threadIdx.x ;
+		key[r] = i<n ? keys[i] : 0ull ;
 	}
-	__syncwarp() ;
-	for ( int d = threadIdx.x ; d<256 ; d += 32 ) counts[size_t( d )*nblocks+blockIdx.x] = hist[d] ;
+#pragma unroll
+	for ( int r = 0 ; r<RTX_RS_TILE/( 32*RTX_RS_WARPS ) ; r++ ) {
+		const uint32_t i = base+uint32_t( r )*32u*RTX_RS_WARPS+threadIdx.x ;
+		if ( i<n ) atomicAdd( hist+uint32_t( ( key[r]>>shift )&255u ), 1u ) ;
+	}
+	__syncthreads() ;
+	for ( int d = threadIdx.x ; d<256 ; d += 32*RTX_RS_WARPS ) counts[size_t( d )*nblocks+blockIdx.x] = hist[d] ;
 }
 // exclusive scan of counts[256*nblocks] (digit-major) in one block
 __global__ void __launch_bounds__( 1024 ) k_radix_scan( uint32_t* counts, uint32_t m ) {
@@ -191,28 +207,46 @@ __global__ void __launch_bounds__( 1024 ) k_radix_scan( uint32_t* counts, uint32
 	uint32_t run = threadIdx.x ? part[threadIdx.x-1] : 0u ;
 	for ( uint32_t i = a ; i<b ; i++ ) { const uint32_t c = counts[i] ; counts[i] = run ; run += c ; }
 }
-__global__ void __launch_bounds__( 32 ) k_radix_scatter( const uint64_t* keys, const uint32_t* vals, uint32_t n, int shift, const uint32_t* offsets, uint32_t nblocks, uint64_t* keys_out, uint32_t* vals_out ) {
-	__shared__ uint32_t off[256] ;
-	for ( int d = threadIdx.x ; d<256 ; d += 32 ) off[d] = offsets[size_t( d )*nblocks+blockIdx.x] ;
-	__syncwarp() ;
-	const uint32_t lane = threadIdx.x ;
-	const uint32_t base = blockIdx.x*RTX_RS_TILE ;
-	for ( uint32_t k = 0 ; k<RTX_RS_TILE ; k += 32 ) {
-		const uint32_t i = base+k+lane ;
-		const bool act = i<n ;
+__global__ void __launch_bounds__( 32*RTX_RS_WARPS ) k_radix_scatter( const uint64_t* keys, const uint32_t* vals, uint32_t n, int shift, const uint32_t* offsets, uint32_t nblocks, uint64_t* keys_out, uint32_t* vals_out ) {
+	__shared__ uint32_t off[RTX_RS_WARPS][256] ;
+	const uint32_t lane = threadIdx.x&31u, warp = threadIdx.x>>5 ;
+	for ( int d = threadIdx.x ; d<256*RTX_RS_WARPS ; d += 32*RTX_RS_WARPS ) ( &off[0][0] )[d] = 0 ;
+	__syncthreads() ;
+	// this warp's run of the tile, in registers
+	const uint32_t base = blockIdx.x*RTX_RS_TILE+warp*( RTX_RS_TILE/RTX_RS_WARPS ) ;
+	uint64_t key[RTX_RS_ROUNDS] ;
+	uint32_t val[RTX_RS_ROUNDS] ;
+#pragma unroll
+	for ( int r = 0 ; r<RTX_RS_ROUNDS ; r++ ) {
+		const uint32_t i = base+uint32_t( r )*32u+lane ;
+		key[r] = i<n ? keys[i] : 0ull ;
+		val[r] = i<n ? vals[i] : 0u ;
+	}
+#pragma unroll
+	for ( int r = 0 ; r<RTX_RS_ROUNDS ; r++ )
+		if ( base+uint32_t( r )*32u+lane<n ) atomicAdd( &off[warp][uint32_t( ( key[r]>>shift )&255u )], 1u ) ;
+	__syncthreads() ;
+	// digit d: tile offset, then the counts of the warps in front
+	for ( int d = threadIdx.x ; d<256 ; d += 32*RTX_RS_WARPS ) {
+		uint32_t run = offsets[size_t( d )*nblocks+blockIdx.x] ;
+#pragma unroll
+		for ( int w = 0 ; w<RTX_RS_WARPS ; w++ ) { const uint32_t c = off[w][d] ; off[w][d] = run ; run += c ; }
+	}
+	__syncthreads() ;
+#pragma unroll
+	for ( int r = 0 ; r<RTX_RS_ROUNDS ; r++ ) {
+		const bool act = base+uint32_t( r )*32u+lane<n ;
 		const uint32_t mask = __ballot_sync( 0xffffffffu, act ) ;
-		if ( mask == 0 ) break ;
 		if ( act ) {
-			const uint64_t key = keys[i] ;
-			const uint32_t d = uint32_t( ( key>>shift )&255u ) ;
+			const uint32_t d = uint32_t( ( key[r]>>shift )&255u ) ;
 			const uint32_t peers = __match_any_sync( mask, d ) ;
 			const uint32_t rank = __popc( peers&( ( 1u<<lane )-1u ) ) ;
-			const uint32_t pos = off[d]+rank ;
+			const uint32_t pos = off[warp][d]+rank ;
 			__syncwarp( mask ) ;
-			if ( rank == 0 ) off[d] += __popc( peers ) ;
+			if ( rank == 0 ) off[warp][d] += __popc( peers ) ;
 			__syncwarp( mask ) ;
-			keys_out[pos] = key ;
-			vals_out[pos] = vals[i] ;
+			keys_out[pos] = key[r] ;
+			vals_out[pos] = val[r] ;
 		}
 	}
 }

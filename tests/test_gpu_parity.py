@@ -290,3 +290,24 @@ def test_rtwo_cli_batch_output():
     # analytic mode and a bad option
     r = subprocess.run([exe, "--analytic", "-g", "64x48", "-s", "1", "-q", "-S"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True)
     assert r.stdout == b"" and b"(pixel, rays, milliseconds)" in r.stderr
+
+
+def test_build_stage_times_and_read_probe():
+    """rtx_build_stages / rtx_probe_read (measurement instruments of include/rtx.h)."""
+    sp = scenes.book1(seed=3)
+    ctx = api.Context(0)
+    try:
+        scenes.load(ctx, sp, "mesh", 4)
+        blas, tlas = ctx.build_stages()
+        st = ctx.stats()
+        assert set(blas) == set(api.Context.BUILD_STAGES) == set(tlas)
+        assert all(v >= 0.0 for v in blas.values()) and all(v >= 0.0 for v in tlas.values())
+        assert 0.0 < sum(blas.values()) <= st["ms_build_blas"] * 1.01 + 0.01
+        assert 0.0 < sum(tlas.values()) <= st["ms_build_tlas"] * 1.01 + 0.01
+        ctx.update()
+        _, tl2 = ctx.build_stages()
+        assert tl2["keys"] == 0.0 and tl2["sort"] == 0.0 and tl2["boxes"] + tl2["wide_nodes"] > 0.0
+        gbs = ctx.probe_read(16 << 20, 50)
+        assert gbs > 2000.0            # L2-resident: far above anything a host path could show
+    finally:
+        ctx.close()
