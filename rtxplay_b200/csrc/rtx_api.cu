@@ -360,6 +360,7 @@ FrameArgs frame_args( rtx_ctx* c, const rtx_params* p ) {
 	if ( p->image_w != c->w || p->image_h != c->h || c->w == 0 ) throw std::runtime_error( "rtx: image size differs from the last rtx_resize" ) ;
 	if ( p->image_w<2 || p->image_h<2 ) throw std::runtime_error( "rtx: image must be at least 2x2" ) ;
 	FrameArgs a ;
+	memset( &a, 0, sizeof( a ) ) ;
 	a.S = scene_dev( c ) ; a.cam = camera_dev( p->camera ) ;
 	a.w = p->image_w ; a.h = p->image_h ; a.spp = p->spp ; a.depth = p->depth ; a.seed = p->seed ;
 	a.sample0 = p->sample0 ; a.sample_stride = p->sample_stride ? p->sample_stride : 1u ; a.accumulate = p->accumulate ;
@@ -385,11 +386,12 @@ void do_resolve( rtx_ctx* c, uint64_t total_spp ) {
 }
 
 void do_render( rtx_ctx* c, const rtx_params* p, bool resolve ) {
-	const FrameArgs a = frame_args( c, p ) ;
+	FrameArgs a = frame_args( c, p ) ;
+	unit_plan( a ) ;
 	c->guides_valid = a.guides != 0 ;
 	CK( cudaEventRecord( c->ev0, c->stream ) ) ;
 	if ( a.depth>255u ) throw std::runtime_error( "rtx: depth above 255 is not supported" ) ;
-	const uint32_t n_tiles = ( ( a.w+7u )>>3 )*( ( a.h+3u )>>2 )*( ( a.spp+RTX_UNIT_SPP-1u )/RTX_UNIT_SPP ) ;   // work units
+	const uint32_t n_tiles = ( ( a.w+7u )>>3 )*( ( a.h+3u )>>2 )*( a.chunks_full+a.chunks_taper ) ;   // work units
 	CK( cudaMemsetAsync( c->d_tile_counter, 0, sizeof( uint32_t ), c->stream ) ) ;
 	if ( ! a.accumulate ) {   // paths add into the buffers with atomics: start from zero (optx/camera_i.cu:52)
 		CK( cudaMemsetAsync( c->d_accum, 0, sizeof( uint64_t )*4*size_t( a.w )*a.h, c->stream ) ) ;

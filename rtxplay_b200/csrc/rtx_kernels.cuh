@@ -37,6 +37,7 @@ struct DevStack {
 	}
 } ;
 
+#define RTX_TAPER_MAX 39
 struct FrameArgs {
 	SceneDev  S ;
 	CameraDev cam ;
@@ -50,6 +51,10 @@ struct FrameArgs {
 	float*    hit_t ;    // [w*h]
 	uint32_t  guides ;   // fill the guide layers too
 	long long* guide_acc ; // [6*w*h] fixed-point (2^-30) sums: normal xyz, albedo rgb
+	// work units of k_render (unit_plan): `chunks_full` sample chunks of RTX_UNIT_SPP, then
+	// `chunks_taper` shrinking ones starting at taper_s0[k] (relative to the end of the full ones)
+	uint32_t  chunks_full, chunks_taper ;
+	uint16_t  taper_s0[RTX_TAPER_MAX+1] ;
 } ;
 
 // lane -> pixel: each warp owns an 8x4 tile (primary rays of a warp stay close)
@@ -73,7 +78,7 @@ __device__ __forceinline__ void red_add_u64( unsigned long long* addr, unsigned 
 }
 
 // The path tracer (see rtx_pool.cuh): one warp per CTA, persistent.  Work is handed out in
-// small units -- an 8x4 pixel tile x RTX_UNIT_SPP samples = up to 512 paths -- through a
+// small units -- an 8x4 pixel tile x RTX_UNIT_SPP samples = up to 2048 paths, fewer towards the end -- through a
 // global counter; a warp streams from one unit straight into the next (a lane whose path
 // ends takes the next path of the warp's current unit, whichever tile that is), so no lane
 // idles at tile ends and the kernel's tail is one unit, not one tile of 16 000 paths.  A
@@ -90,10 +95,34 @@ __device__ __forceinline__ void red_add_u64( unsigned long long* addr, unsigned 
 #define RTX_NODE_BIAS 0         // votes added to the node kind
 #endif
 #ifndef RTX_UNIT_SPP
-#define RTX_UNIT_SPP 16u
+#define RTX_UNIT_SPP 64u        // samples per pixel of a full work unit (16-128 measured alike; swept with the taper in place)
 #endif
+#ifndef RTX_UNIT_TAIL
+#define RTX_UNIT_TAIL 2u        // ... of the smallest one
+#endif
+// Work units taper off.  A frame's samples are cut into chunks of RTX_UNIT_SPP, except for the
+// last RTX_UNIT_SPP..2*RTX_UNIT_SPP-1 of them (all of them in a short frame), which go out in
+// chunks that shrink by a quarter of what is left each time, down to RTX_UNIT_TAIL.  Units are
+// handed out chunk by chunk, so the kernel ends on small ones.  Why: per-warp finish times
+// (RTX_DEBUG_TIMES) showed warps working up to 12 ms on their last 512-path unit after the
+// counter had run dry -- a 15 ms tail on every launch, whatever its length; units of 64 paths
+// throughout, on the other hand, trace 17 % slower (a warp that stays on one tile for hundreds
+// of paths keeps its lanes in the same part of the hierarchy).
+inline void unit_plan( FrameArgs& a ) {
+	a.chunks_full = a.spp>RTX_UNIT_SPP ? ( a.spp-RTX_UNIT_SPP )/RTX_UNIT_SPP : 0u ;
+	uint32_t rem = a.spp-a.chunks_full*RTX_UNIT_SPP, s = 0, n = 0 ;
+	while ( rem>0 && n<RTX_TAPER_MAX ) {
+		uint32_t len = ( rem+3u )/4u ;
+		if ( len<RTX_UNIT_TAIL ) len = RTX_UNIT_TAIL ;
+		if ( len>rem || n == RTX_TAPER_MAX-1 ) len = rem ;
+		a.taper_s0[n++] = uint16_t( s ) ;
+		s += len ; rem -= len ;
+	}
+	a.taper_s0[n] = uint16_t( s ) ;
+	a.chunks_taper = n ;
+}
 template <bool GUIDES>
-__global__ void __launch_bounds__( 32, RTX_MIN_CTAS ) k_render( const FrameArgs a, uint32_t* unit_counter, int32_t* ovf_all ) {
+__global__ void __launch_bounds__( 32, RTX_MIN_CTAS ) k_render( const __grid_constant__ FrameArgs a, uint32_t* unit_counter, int32_t* ovf_all ) {
 	const uint32_t lane = threadIdx.x ;
 	const uint32_t lt = ( 1u<<lane )-1u ;
 #if defined( RTX_REGPOOL )
@@ -108,7 +137,7 @@ __global__ void __launch_bounds__( 32, RTX_MIN_CTAS ) k_render( const FrameArgs 
 	p.ovf = ovf_all+size_t( blockIdx.x )*RTX_POOL_R*RTX_POOL_OVF*2 ;
 #endif
 	const uint32_t tiles_x = ( a.w+7u )>>3, tiles_y = ( a.h+3u )>>2, n_tiles = tiles_x*tiles_y ;
-	const uint32_t n_chunks = ( a.spp+RTX_UNIT_SPP-1u )/RTX_UNIT_SPP ;
+	const uint32_t n_chunks = a.chunks_full+a.chunks_taper ;
 	const uint32_t n_units = n_tiles*n_chunks ;   // unit u: chunk u/n_tiles of tile u%n_tiles
 	unsigned long long* accum = reinterpret_cast<unsigned long long*>( a.accum ) ;
 	unsigned long long* guide = reinterpret_cast<unsigned long long*>( a.guide_acc ) ;
@@ -120,6 +149,11 @@ __global__ void __launch_bounds__( 32, RTX_MIN_CTAS ) k_render( const FrameArgs 
 	int kinds[RTX_K] ;
 #pragma unroll
 	for ( int j = 0 ; j<RTX_K ; j++ ) kinds[j] = K_REGEN ;
+#if defined( RTX_DEBUG_TIMES )
+	// development instrument: when this warp started, ran out of units, ended (ns) -> hit_id[3*warp..]
+	unsigned long long dbg_t0, dbg_tx = 0 ;
+	asm volatile( "mov.u64 %0, %globaltimer;" : "=l"( dbg_t0 ) ) ;
+#endif
 
 	while ( true ) {
 		// vote: which step kind can most lanes take?
@@ -204,14 +238,24 @@ __global__ void __launch_bounds__( 32, RTX_MIN_CTAS ) k_render( const FrameArgs 
 						uint32_t u = 0 ;
 						if ( lane == 0 ) u = atomicAdd( unit_counter, 1u ) ;
 						u = __shfl_sync( 0xffffffffu, u, 0 ) ;
-						if ( u>=n_units )
+						if ( u>=n_units ) {
 							exhausted = true ;
+#if defined( RTX_DEBUG_TIMES )
+							asm volatile( "mov.u64 %0, %globaltimer;" : "=l"( dbg_tx ) ) ;
+#endif
+						}
 						else {
 							const uint32_t tile = u%n_tiles, chunk = u/n_tiles ;
 							unit_x0 = ( tile%tiles_x )*8u ; unit_y0 = ( tile/tiles_x )*4u ;
+							uint32_t len = RTX_UNIT_SPP ;
 							unit_s0 = chunk*RTX_UNIT_SPP ;
+							if ( chunk>=a.chunks_full ) {
+								const uint32_t k = chunk-a.chunks_full ;
+								unit_s0 = a.chunks_full*RTX_UNIT_SPP+a.taper_s0[k] ;
+								len = uint32_t( a.taper_s0[k+1] )-uint32_t( a.taper_s0[k] ) ;
+							}
 							unit_pos = 0 ;
-							unit_left = 32u*min( RTX_UNIT_SPP, a.spp-unit_s0 ) ;
+							unit_left = 32u*len ;
 						}
 					}
 					if ( exhausted ) {
@@ -238,6 +282,13 @@ __global__ void __launch_bounds__( 32, RTX_MIN_CTAS ) k_render( const FrameArgs 
 #pragma unroll
 		for ( int jj = 0 ; jj<RTX_K ; jj++ ) if ( jj == j ) kinds[jj] = nk ;
 	}
+#if defined( RTX_DEBUG_TIMES )
+	if ( lane == 0 && a.hit_id ) {
+		unsigned long long t1 ;
+		asm volatile( "mov.u64 %0, %globaltimer;" : "=l"( t1 ) ) ;
+		a.hit_id[3*blockIdx.x] = int64_t( dbg_t0 ) ; a.hit_id[3*blockIdx.x+1] = int64_t( dbg_tx ) ; a.hit_id[3*blockIdx.x+2] = int64_t( t1 ) ;
+	}
+#endif
 }
 
 // first hit of the primary ray of sample `sample0` of every pixel

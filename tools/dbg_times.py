@@ -1,0 +1,18 @@
+import sys, numpy as np
+sys.path.insert(0, '.')
+from rtxplay_b200 import api, scenes
+sp = scenes.book1(seed=1)
+ctx = api.Context(0)
+scenes.load(ctx, sp, "mesh", None)
+w, h = 1200, 800
+ctx.resize(w, h)
+cam = api.camera(aspratio=w / h)
+for spp in (16, 16, 64):
+    ctx.render(ctx.params(cam, spp))
+    ms = ctx.last_render_ms()
+    t = ctx.read(api.BUF_HIT_ID).reshape(-1)[:3 * 2960].reshape(-1, 3).astype(np.int64)
+    t0 = t[:, 0].min()
+    st, ex, en = (t[:, 0] - t0) / 1e6, (t[:, 1] - t0) / 1e6, (t[:, 2] - t0) / 1e6
+    pc = lambda a: [round(float(np.percentile(a, q)), 2) for q in (0, 10, 50, 90, 99, 100)]
+    print("spp", spp, "kernel ms %.2f" % ms, "start", pc(st), "exhausted", pc(ex), "end", pc(en))
+ctx.close()
