@@ -391,7 +391,7 @@ void do_render( rtx_ctx* c, const rtx_params* p, bool resolve ) {
 	c->guides_valid = a.guides != 0 ;
 	CK( cudaEventRecord( c->ev0, c->stream ) ) ;
 	if ( a.depth>255u ) throw std::runtime_error( "rtx: depth above 255 is not supported" ) ;
-	const uint32_t n_tiles = ( ( a.w+7u )>>3 )*( ( a.h+3u )>>2 )*( a.chunks_full+a.chunks_taper ) ;   // work units
+	const uint32_t n_tiles = ( ( a.w+RTX_TILE_W-1u )>>RTX_TILE_WLOG )*( ( a.h+RTX_TILE_H-1u )>>RTX_TILE_HLOG )*( a.chunks_full+a.chunks_taper ) ;   // work units
 	CK( cudaMemsetAsync( c->d_tile_counter, 0, sizeof( uint32_t ), c->stream ) ) ;
 	if ( ! a.accumulate ) {   // paths add into the buffers with atomics: start from zero (optx/camera_i.cu:52)
 		CK( cudaMemsetAsync( c->d_accum, 0, sizeof( uint64_t )*4*size_t( a.w )*a.h, c->stream ) ) ;

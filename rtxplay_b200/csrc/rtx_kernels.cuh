@@ -97,6 +97,16 @@ __device__ __forceinline__ void red_add_u64( unsigned long long* addr, unsigned 
 #ifndef RTX_UNIT_SPP
 #define RTX_UNIT_SPP 64u        // samples per pixel of a full work unit (16-128 measured alike; swept with the taper in place)
 #endif
+#ifndef RTX_TILE_WLOG
+#define RTX_TILE_WLOG 3         // a unit's pixels: a tile of 2^WLOG x 2^HLOG (at most 32) ...
+#endif
+#ifndef RTX_TILE_HLOG
+#define RTX_TILE_HLOG 2
+#endif
+#define RTX_TILE_W ( 1u<<RTX_TILE_WLOG )
+#define RTX_TILE_H ( 1u<<RTX_TILE_HLOG )
+#define RTX_TILE_PLOG ( RTX_TILE_WLOG+RTX_TILE_HLOG )
+#define RTX_TILE_P ( 1u<<RTX_TILE_PLOG )
 #ifndef RTX_UNIT_TAIL
 #define RTX_UNIT_TAIL 2u        // ... of the smallest one
 #endif
@@ -136,7 +146,7 @@ __global__ void __launch_bounds__( 32, RTX_MIN_CTAS ) k_render( const __grid_con
 	p.w = words ;
 	p.ovf = ovf_all+size_t( blockIdx.x )*RTX_POOL_R*RTX_POOL_OVF*2 ;
 #endif
-	const uint32_t tiles_x = ( a.w+7u )>>3, tiles_y = ( a.h+3u )>>2, n_tiles = tiles_x*tiles_y ;
+	const uint32_t tiles_x = ( a.w+RTX_TILE_W-1u )>>RTX_TILE_WLOG, tiles_y = ( a.h+RTX_TILE_H-1u )>>RTX_TILE_HLOG, n_tiles = tiles_x*tiles_y ;
 	const uint32_t n_chunks = a.chunks_full+a.chunks_taper ;
 	const uint32_t n_units = n_tiles*n_chunks ;   // unit u: chunk u/n_tiles of tile u%n_tiles
 	unsigned long long* accum = reinterpret_cast<unsigned long long*>( a.accum ) ;
@@ -246,7 +256,7 @@ __global__ void __launch_bounds__( 32, RTX_MIN_CTAS ) k_render( const __grid_con
 						}
 						else {
 							const uint32_t tile = u%n_tiles, chunk = u/n_tiles ;
-							unit_x0 = ( tile%tiles_x )*8u ; unit_y0 = ( tile/tiles_x )*4u ;
+							unit_x0 = ( tile%tiles_x )<<RTX_TILE_WLOG ; unit_y0 = ( tile/tiles_x )<<RTX_TILE_HLOG ;
 							uint32_t len = RTX_UNIT_SPP ;
 							unit_s0 = chunk*RTX_UNIT_SPP ;
 							if ( chunk>=a.chunks_full ) {
@@ -255,7 +265,7 @@ __global__ void __launch_bounds__( 32, RTX_MIN_CTAS ) k_render( const __grid_con
 								len = uint32_t( a.taper_s0[k+1] )-uint32_t( a.taper_s0[k] ) ;
 							}
 							unit_pos = 0 ;
-							unit_left = 32u*len ;
+							unit_left = RTX_TILE_P*len ;
 						}
 					}
 					if ( exhausted ) {
@@ -269,8 +279,8 @@ __global__ void __launch_bounds__( 32, RTX_MIN_CTAS ) k_render( const __grid_con
 						// path idx of the unit -> (sample, pixel of the tile); pixels beyond the image
 						// border are skipped (the lane asks again)
 						const uint32_t idx = unit_pos+rank ;
-						const uint32_t px = idx&31u, smp = unit_s0+( idx>>5 ) ;
-						const uint32_t x = unit_x0+( px&7u ), y = unit_y0+( px>>3 ) ;
+						const uint32_t px = idx&( RTX_TILE_P-1u ), smp = unit_s0+( idx>>RTX_TILE_PLOG ) ;
+						const uint32_t x = unit_x0+( px&( RTX_TILE_W-1u ) ), y = unit_y0+( px>>RTX_TILE_WLOG ) ;
 						if ( x<a.w && y<a.h )
 							nk = step_regen( p, slot, a.S, a.cam, x, y, a.w, a.h, a.w*y+x, a.seed, a.sample0+smp*a.sample_stride, a.depth ) ;
 					}
