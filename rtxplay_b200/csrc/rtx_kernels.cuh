@@ -89,7 +89,8 @@ __device__ __forceinline__ void red_add_u64( unsigned long long* addr, unsigned 
 #define RTX_STICKY 5           // keep doing node steps while at least this many lanes have one (swept: 4-6 best)
 #endif
 #ifndef RTX_MIN_CTAS
-#define RTX_MIN_CTAS 20         // resident render warps per SM the register budget is set for (96 registers)
+#define RTX_MIN_CTAS 18         // launch bound: 17-20 all compile to 96 registers = 5 warps per scheduler, 20 per SM (24 at 80
+                                // registers measure 9 % slower); 18/19 happen to schedule the code 4 % better than 20
 #endif
 #ifndef RTX_NODE_BIAS
 #define RTX_NODE_BIAS 0         // votes added to the node kind
@@ -97,6 +98,16 @@ __device__ __forceinline__ void red_add_u64( unsigned long long* addr, unsigned 
 #ifndef RTX_UNIT_SPP
 #define RTX_UNIT_SPP 64u        // samples per pixel of a full work unit (16-128 measured alike; swept with the taper in place)
 #endif
+#ifndef RTX_SM_SUPER
+#define RTX_SM_SUPER 1          // the warps of an SM draw their units from a shared block of adjacent tiles
+#endif
+#ifndef RTX_SUPER_BWLOG
+#define RTX_SUPER_BWLOG 1       // an SM's shared block: 2^BWLOG x 2^BHLOG tiles x 32/(tiles) consecutive sample chunks
+#endif
+#ifndef RTX_SUPER_BHLOG
+#define RTX_SUPER_BHLOG 1
+#endif
+#define RTX_SUPER_CG ( 32u>>( RTX_SUPER_BWLOG+RTX_SUPER_BHLOG ) )
 #ifndef RTX_TILE_WLOG
 #define RTX_TILE_WLOG 3         // a unit's pixels: a tile of 2^WLOG x 2^HLOG (at most 32) ...
 #endif
@@ -149,6 +160,12 @@ __global__ void __launch_bounds__( 32, RTX_MIN_CTAS ) k_render( const __grid_con
 	const uint32_t tiles_x = ( a.w+RTX_TILE_W-1u )>>RTX_TILE_WLOG, tiles_y = ( a.h+RTX_TILE_H-1u )>>RTX_TILE_HLOG, n_tiles = tiles_x*tiles_y ;
 	const uint32_t n_chunks = a.chunks_full+a.chunks_taper ;
 	const uint32_t n_units = n_tiles*n_chunks ;   // unit u: chunk u/n_tiles of tile u%n_tiles
+#if RTX_SM_SUPER
+	const uint32_t supers_x = ( tiles_x+( 1u<<RTX_SUPER_BWLOG )-1u )>>RTX_SUPER_BWLOG, n_supers = supers_x*( ( tiles_y+( 1u<<RTX_SUPER_BHLOG )-1u )>>RTX_SUPER_BHLOG ) ;
+	uint32_t smid ;
+	asm( "mov.u32 %0, %smid;" : "=r"( smid ) ) ;
+	smid &= 255u ;   // (256 per-SM words are allocated)
+#endif
 	unsigned long long* accum = reinterpret_cast<unsigned long long*>( a.accum ) ;
 	unsigned long long* guide = reinterpret_cast<unsigned long long*>( a.guide_acc ) ;
 
@@ -246,8 +263,39 @@ __global__ void __launch_bounds__( 32, RTX_MIN_CTAS ) k_render( const __grid_con
 				while ( want ) {
 					if ( unit_left == 0 && ! exhausted ) {
 						uint32_t u = 0 ;
+#if RTX_SM_SUPER
+						// the warps of an SM share a block of 8x4 adjacent tiles (one chunk of samples): what one
+						// warp pulls into L1 the others use.  Per-SM word: (block+1)<<32 | next tile of the block;
+						// the warp that draws the first index past the block fetches the SM's next block from the
+						// global counter, the others retry until it is installed.
+						if ( lane == 0 ) {
+							unsigned long long* state = reinterpret_cast<unsigned long long*>( unit_counter+2 )+smid ;
+							while ( true ) {
+								const unsigned long long old = atomicAdd( state, 1ull ) ;
+								const uint32_t hi = uint32_t( old>>32 ), idx = uint32_t( old ) ;
+								if ( hi == 0xffffffffu ) { u = 0xffffffffu ; break ; }
+								if ( hi != 0u && idx<32u ) {
+									const uint32_t g = hi-1u, cg = g/n_supers, st = g%n_supers ;
+									const uint32_t ti = idx&( ( 1u<<( RTX_SUPER_BWLOG+RTX_SUPER_BHLOG ) )-1u ) ;
+									const uint32_t chunk = cg*RTX_SUPER_CG+( idx>>( RTX_SUPER_BWLOG+RTX_SUPER_BHLOG ) ) ;
+									const uint32_t tx = ( ( st%supers_x )<<RTX_SUPER_BWLOG )+( ti&( ( 1u<<RTX_SUPER_BWLOG )-1u ) ), ty = ( ( st/supers_x )<<RTX_SUPER_BHLOG )+( ti>>RTX_SUPER_BWLOG ) ;
+									u = ( tx<tiles_x && ty<tiles_y && chunk<n_chunks ) ? chunk*n_tiles+ty*tiles_x+tx : 0xfffffffeu ;   // (..fe: beyond the image edge / the last chunk)
+									break ;
+								}
+								if ( ( hi == 0u && idx == 0u ) || ( hi != 0u && idx == 32u ) ) {
+									const uint32_t g = atomicAdd( unit_counter, 1u ) ;
+									atomicExch( state, g<n_supers*( ( n_chunks+RTX_SUPER_CG-1u )/RTX_SUPER_CG ) ? ( ( unsigned long long )( g+1u )<<32 ) : 0xffffffff00000000ull ) ;
+								} else
+									__nanosleep( 100 ) ;
+							}
+						}
+						u = __shfl_sync( 0xffffffffu, u, 0 ) ;
+						if ( u == 0xfffffffeu )
+							continue ;
+#else
 						if ( lane == 0 ) u = atomicAdd( unit_counter, 1u ) ;
 						u = __shfl_sync( 0xffffffffu, u, 0 ) ;
+#endif
 						if ( u>=n_units ) {
 							exhausted = true ;
 #if defined( RTX_DEBUG_TIMES )

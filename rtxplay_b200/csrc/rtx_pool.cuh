@@ -32,7 +32,9 @@ namespace rtx {
 #if RTX_K == 1 && ! defined( RTX_REGPOOL )
 #define RTX_REGPOOL 1
 #endif
+#ifndef RTX_POOL_STACK
 #define RTX_POOL_STACK 16       // stack entries (work item + its entry distance) per slot kept in shared memory
+#endif
 #define RTX_POOL_OVF   80       // further entries per slot in a global overflow area
 
 // slot fields (32-bit words)
