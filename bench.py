@@ -14,6 +14,8 @@ triangles), 1200x800, 500 spp, depth 50, defocus blur on.  One "step" = one fram
              rtx_postproc + rtx_read of the 8-bit image into host memory).
   roofline   dominant kernel k_render: algorithmic bytes per segment of SURVEY.md 8(d)
              (64*ceil(log2 N) + 48 + 128) x segments per launch / its CUDA-event duration.
+  roofline.counted  work per segment from the kernel's own node-visit / primitive-test counters
+             (instrumented build librtx_count.so, one short frame in a child process, untimed).
   cpu_baseline  the oracle's double-precision port of rtow.cxx (the reference's CPU path:
              analytic spheres, exhaustive scan) on a bounded sample, all host threads.
 
@@ -55,6 +57,9 @@ def parse():
     ap.add_argument("--scene", default="book1", help="book1 (default) or grid<N>: N x N field of small spheres (stress scene, BASELINE configs[4])")
     ap.add_argument("--cpu-spp", type=int, default=2, help="samples per pixel of the CPU baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-count", action="store_true", help="skip the counted-work leg (instrumented library)")
+    ap.add_argument("--count-spp", type=int, default=4, help="samples per pixel of the counted-work frame")
+    ap.add_argument("--count-worker", action="store_true", help=argparse.SUPPRESS)
     return ap.parse_args()
 
 
@@ -112,6 +117,51 @@ def run_reference(a):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------- counted work
+def count_worker(a):
+    """Runs in a child process with RTX_LIB = librtx_count.so (the instrumented build): one frame
+    of the same scene at --count-spp, traversal events from the kernel's own counters."""
+    from rtxplay_b200 import api, scenes
+    ctx = api.Context(int(os.environ.get("LOCAL_RANK", "0")))
+    scenes.load(ctx, make_scene(a), a.mode, a.ndiv if a.scene == "book1" else None)
+    ctx.resize(a.width, a.height)
+    ctx.counters(reset=True)
+    ctx.render(ctx.params(api.camera(aspratio=a.width / a.height), a.count_spp, a.depth, seed=a.seed))
+    c = ctx.counters()
+    c["segments"] = ctx.stats()["segments"]
+    ctx.close()
+    print("COUNTED " + json.dumps(c), flush=True)
+
+
+def counted_leg(a):
+    """work per segment from the kernel's own node-visit / primitive-test counters,
+    in the FLOP and byte conventions of the model (box test 23 flop, triangle 56, sphere 29, shading
+    60; a node record 128 B, a triangle record 64 B, a thing's traversal record 128 + 16 B)."""
+    lib = os.path.join(ROOT, "rtxplay_b200", "librtx_count.so")
+    if not os.path.exists(lib):
+        return {"unavailable": "librtx_count.so not built"}
+    argv = [sys.executable, os.path.abspath(__file__), "--count-worker", "--width", str(a.width), "--height", str(a.height), "--depth", str(a.depth),
+            "--mode", a.mode, "--seed", str(a.seed), "--scene", a.scene, "--count-spp", str(a.count_spp)] + (["--ndiv", str(a.ndiv)] if a.ndiv is not None else [])
+    try:
+        out = subprocess.run(argv, env=dict(os.environ, RTX_LIB=lib), capture_output=True, text=True, timeout=300)
+        c = json.loads([l for l in out.stdout.splitlines() if l.startswith("COUNTED ")][-1][8:])
+    except Exception as e:                                   # an instrument: its failure must not cost the bench line
+        return {"unavailable": "counted-work run failed: %s" % e}
+    n = float(max(c["segments"], 1))
+    nodes, leaves, tris, things = c["nodes"] / n, c["leaves"] / n, c["tris"] / n, c["things"] / n
+    other = c["culled_or_sphere_tests"] / n
+    if a.mode == "mesh":
+        flop = 92 * nodes + 56 * tris + 25 * things + 60
+        byts = 128 * nodes + 64 * tris + 16 * things + 128 * (things - other) + 128
+    else:
+        flop = 92 * nodes + 29 * other + 60
+        byts = 128 * nodes + 32 * things + 128
+    return {"sample": "%dx%d, %d spp, instrumented build (one global atomic per event)" % (a.width, a.height, a.count_spp),
+            "segments": c["segments"], "node_steps_per_segment": nodes, "leaf_steps_per_segment": leaves, "triangle_tests_per_segment": tris,
+            "thing_visits_per_segment": things, ("culled_visits_per_segment" if a.mode == "mesh" else "sphere_tests_per_segment"): other,
+            "flop_per_segment": flop, "bytes_per_segment": byts}
 
 
 # ------------------------------------------------------------------------- clocks
@@ -290,6 +340,14 @@ def run_b200(a):
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if not a.no_count and world == 1:
+            cnt = counted_leg(a)
+            if "flop_per_segment" in cnt:
+                cnt["achieved_tflops"] = segs_launch * cnt["flop_per_segment"] / (k_ms * 1e-3) / 1e12
+                cnt["frac_fp32"] = cnt["achieved_tflops"] / fp32_peak
+                cnt["achieved_gbs"] = segs_launch * cnt["bytes_per_segment"] / (k_ms * 1e-3) / 1e9
+                cnt["frac_l2"] = cnt["achieved_gbs"] / l2_peak if l2_peak else None
+            line["roofline"]["counted"] = cnt
         if not a.no_cpu and world == 1:
             v, cores, desc, _ = cpu_leg(a, a.cpu_spp)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
@@ -304,7 +362,9 @@ def run_b200(a):
 
 def main():
     a = parse()
-    if a.impl == "reference":
+    if a.count_worker:
+        count_worker(a)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_b200(a)

@@ -150,6 +150,13 @@ int rtx_build_stages( rtx_ctx* ctx, float blas_ms[5], float tlas_ms[5] ) ;
 /* device time (CUDA events on the launching stream) of the path-tracing kernel of the last
  * rtx_render / rtx_render_accumulate -- the window optx/rtwo.cxx:542-546 times; no device work */
 int rtx_last_render_ms( rtx_ctx* ctx, float* ms ) ;
+/* measurement instrument (SURVEY.md 8(d) "counted" work): traversal events since the last reset --
+ * [0] rays (segments), [1] node steps (4 box tests each), [2] leaf steps, [3] triangle tests,
+ * [4] top-level leaf visits, [5] of those culled by the bounding-sphere pre-test (analytic scenes:
+ * sphere tests), [6] mesh entries of the parity instruments.  Only the instrumented build
+ * (librtx_count.so, -DRTX_DEVICE_COUNTERS: one global atomic per event) counts; in librtx.so the
+ * call fails with a message.  The reference has no counterpart. */
+int rtx_counters_get( rtx_ctx* ctx, uint64_t out[8], int reset ) ;
 
 /* host helpers shared by the C++ shims and the tests (no device work) */
 /* Camera::set, optx/camera.h:30-48 */

@@ -39,7 +39,7 @@ SYMBOLS = [
     "rtx_thing_set_xf", "rtx_thing_get_xf", "rtx_thing_set_optics", "rtx_accel_build", "rtx_accel_refit",
     "rtx_resize", "rtx_render", "rtx_render_accumulate", "rtx_resolve", "rtx_pick", "rtx_postproc",
     "rtx_postproc_dev", "rtx_primary_hits", "rtx_trace_rays", "rtx_read", "rtx_device_ptr", "rtx_write",
-    "rtx_stats_get", "rtx_probe_read", "rtx_build_stages", "rtx_last_render_ms", "rtx_camera_set", "rtx_sphere_mesh",
+    "rtx_stats_get", "rtx_probe_read", "rtx_build_stages", "rtx_last_render_ms", "rtx_counters_get", "rtx_camera_set", "rtx_sphere_mesh",
 ]
 
 

@@ -201,6 +201,14 @@ class Context:
         self._ck(self._L.rtx_probe_read(self._c, ctypes.c_size_t(nbytes), ctypes.c_uint32(repeats), ctypes.byref(g)))
         return g.value
 
+    COUNTERS = ("rays", "nodes", "leaves", "tris", "things", "culled_or_sphere_tests", "entries")
+
+    def counters(self, reset=True):
+        """Traversal events since the last reset (instrumented build librtx_count.so only)."""
+        out = (ctypes.c_uint64 * 8)()
+        self._ck(self._L.rtx_counters_get(self._c, out, ctypes.c_int(1 if reset else 0)))
+        return dict(zip(self.COUNTERS, [int(v) for v in out]))
+
     BUILD_STAGES = ("keys", "sort", "hierarchy", "boxes", "wide_nodes")
 
     def build_stages(self):

@@ -854,4 +854,22 @@ int rtx_last_render_ms( rtx_ctx* c, float* ms ) {
 	RTX_END( c )
 }
 
+int rtx_counters_get( rtx_ctx* c, uint64_t out[8], int reset ) {
+	RTX_TRY( c )
+#if defined( RTX_DEVICE_COUNTERS )
+	unsigned long long v[DC_N] ;
+	CK( cudaStreamSynchronize( c->stream ) ) ;
+	CK( cudaMemcpyFromSymbol( v, g_dev_counts, sizeof( v ) ) ) ;
+	for ( int k = 0 ; k<8 ; k++ ) out[k] = k<DC_N ? uint64_t( v[k] ) : 0u ;
+	if ( reset ) {
+		memset( v, 0, sizeof( v ) ) ;
+		CK( cudaMemcpyToSymbol( g_dev_counts, v, sizeof( v ) ) ) ;
+	}
+#else
+	( void ) out ; ( void ) reset ;
+	throw std::runtime_error( "this library was built without RTX_DEVICE_COUNTERS (use librtx_count.so)" ) ;
+#endif
+	RTX_END( c )
+}
+
 } // extern "C"

@@ -42,6 +42,9 @@
 #define RTX_ANY( pred ) ( pred )
 #endif
 
+#if defined( RTX_DEVICE_COUNTERS ) && defined( __CUDACC__ )
+namespace rtx { enum { DC_rays, DC_nodes, DC_leaves, DC_tris, DC_things, DC_spheres, DC_enters, DC_N } ; __device__ unsigned long long g_dev_counts[DC_N] ; }   // (librtx has one CUDA translation unit)
+#endif
 // traversal statistics for the host harness (compiled out of the product)
 #if defined( RTX_STATS )
 namespace rtx { struct Stats { unsigned long long rays, nodes, leaves, tris, things, spheres, enters, pushes, maxsp ; } ; extern Stats g_stats ; }
@@ -51,6 +54,12 @@ namespace rtx { void trace_event( char c ) ; }
 #define RTX_EVENT( c ) rtx::trace_event( c )
 #define RTX_COUNT( f ) ( rtx::g_stats.f++ )
 #define RTX_COUNT_MAX( f, v ) do { if ( ( unsigned long long )( v )>rtx::g_stats.f ) rtx::g_stats.f = ( v ) ; } while ( 0 )
+#elif defined( RTX_DEVICE_COUNTERS ) && defined( __CUDA_ARCH__ )
+// instrumented build (librtx_count.so, bench.py "counted"): the same events counted on the
+// device with global atomics -- a measuring instrument, far too slow for the product library
+#define RTX_EVENT( c ) ( ( void ) 0 )
+#define RTX_COUNT( f ) ( ( void ) atomicAdd( &rtx::g_dev_counts[rtx::DC_##f], 1ull ) )
+#define RTX_COUNT_MAX( f, v ) ( ( void ) 0 )
 #else
 #define RTX_EVENT( c ) ( ( void ) 0 )
 #define RTX_COUNT( f ) ( ( void ) 0 )
@@ -149,7 +158,9 @@ struct q4 { float x, y, z, w ; } ;   // 16-byte record, bit-compatible with floa
 #define RTX_NODE_RECS  8
 #define RTX_TRI_RECS   4            // a triangle: (a, prim id) (e1, b.x) (e2, b.y) (b.z, c) = 64 bytes, two 256-bit loads
 #define RTX_WIDTH      4
-#define RTX_LEAF_MAX   4            // triangles per mesh leaf (top level: 1 thing per leaf)
+#ifndef RTX_LEAF_MAX
+#define RTX_LEAF_MAX   4            // triangles per mesh leaf, at most 8 (top level: 1 thing per leaf)
+#endif
 #define RTX_REF_EMPTY  0x7ffffffd
 #define RTX_STK_DONE   0x7ffffffe   // bottom of the stack
 #define RTX_STK_RETURN 0x7fffffff   // leave the mesh, back to the top level
@@ -211,15 +222,31 @@ RTX_HD q4 ldq( const q4* p ) {
 // whole 128-byte node touches its cache line 4 times instead of 7 -- the L1 tag stage was a
 // co-bottleneck of the traversal (ncu: l1tex throughput 47 %)
 struct o8 { q4 a, b ; } ;
-RTX_HD o8 ldo( const q4* p ) {
-	o8 r ;
-#if defined( __CUDA_ARCH__ )
-	asm( "ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-		: "=f"( r.a.x ), "=f"( r.a.y ), "=f"( r.a.z ), "=f"( r.a.w ), "=f"( r.b.x ), "=f"( r.b.y ), "=f"( r.b.z ), "=f"( r.b.w ) : "l"( p ) ) ;
-#else
-	r.a = p[0] ; r.b = p[1] ;
+// L1 policy of the node / triangle fetches (tuning knobs; default: the plain non-coherent load)
+#ifndef RTX_NODE_LD
+#define RTX_NODE_LD "ld.global.nc.v8.f32"
 #endif
+#ifndef RTX_TRI_LD
+#define RTX_TRI_LD "ld.global.nc.v8.f32"
+#endif
+#define RTX_LDO_BODY( INSN )                                                                                   \
+	o8 r ;                                                                                                     \
+	asm( INSN " {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                                                              \
+		: "=f"( r.a.x ), "=f"( r.a.y ), "=f"( r.a.z ), "=f"( r.a.w ), "=f"( r.b.x ), "=f"( r.b.y ), "=f"( r.b.z ), "=f"( r.b.w ) : "l"( p ) ) ; \
 	return r ;
+RTX_HD o8 ldo( const q4* p ) {
+#if defined( __CUDA_ARCH__ )
+	RTX_LDO_BODY( RTX_NODE_LD )
+#else
+	o8 r ; r.a = p[0] ; r.b = p[1] ; return r ;
+#endif
+}
+RTX_HD o8 ldo_tri( const q4* p ) {
+#if defined( __CUDA_ARCH__ )
+	RTX_LDO_BODY( RTX_TRI_LD )
+#else
+	o8 r ; r.a = p[0] ; r.b = p[1] ; return r ;
+#endif
 }
 // __ldg has no pointer overload: read the 8 bytes as an integer
 template <class T> RTX_HD const T* ldptr( const T* const* pp ) {
@@ -323,7 +350,11 @@ RTX_HD float safe_rcp( float d ) {
 	// 1/d clamped to +-1e30: a zero component gives a huge finite slope instead of inf, so
 	// that o*idir and the slab products stay finite (no inf-inf, no 0*inf)
 #if defined( __CUDA_ARCH__ )
-	return fminf( fmaxf( __fdividef( 1.f, d ), -1e30f ), 1e30f ) ;
+	// one MUFU.RCP: flushing a denormal d to zero gives +-inf, which the clamp turns into the
+	// same +-1e30 as its huge reciprocal (the non-flushing form costs four more instructions)
+	float r ;
+	asm( "rcp.approx.ftz.f32 %0, %1;" : "=f"( r ) : "f"( d ) ) ;
+	return fminf( fmaxf( r, -1e30f ), 1e30f ) ;
 #else
 	return fminf( fmaxf( 1.f/d, -1e30f ), 1e30f ) ;
 #endif
@@ -412,7 +443,7 @@ RTX_HD void closest( const SceneDev& S, const f3& o, const f3& d, float tmin, St
 				for ( uint32_t k = 0 ; k<count ; k++ ) {
 					RTX_COUNT( tris ) ;
 					const q4* T = tris+size_t( first+k )*RTX_TRI_RECS ;
-					const o8 t01 = ldo( T ), t23 = ldo( T+2 ) ;
+					const o8 t01 = ldo_tri( T ), t23 = ldo_tri( T+2 ) ;
 					const q4 a = t01.a, b = t01.b, c = t23.a ;
 					float t, u, v ;
 					if ( tri_test( mk3( a.x, a.y, a.z ), mk3( b.x, b.y, b.z ), mk3( c.x, c.y, c.z ), ohi, olo, dd, tmin, t, u, v ) ) {
@@ -570,18 +601,21 @@ RTX_HD float schlick( float cos_theta, float ratio ) {                          
 // the path is absorbed.
 RTX_HD_CALL bool scatter( const ThingShade* ts, const f3& dir, const Frame& fr, Pcg& rng, f3& attened, f3& out ) {
 	const int32_t type = RTX_LDG( &ts->type ) ;
-	if ( type == 0 ) {
-		f3 dnew = fr.normal+rng.rndVon1sphere() ;
-		if ( fabsf( dnew.x )<1e-8f && fabsf( dnew.y )<1e-8f && fabsf( dnew.z )<1e-8f )   // util.h:8 kNear0
-			dnew = fr.normal ;
-		out = dnew ;
+	if ( type != 2 ) {
+		// Diffuse and Reflect both start with one rndVin1sphere(): the lanes of a warp run that
+		// rejection loop -- the longest piece of shading, and as long as its slowest lane -- together
+		// instead of once per material branch.  Per path the draws and their order are unchanged.
+		const f3 s = rng.rndVin1sphere() ;
 		attened = mk3( RTX_LDG( ts->albedo ), RTX_LDG( ts->albedo+1 ), RTX_LDG( ts->albedo+2 ) ) ;
-		return true ;
-	}
-	if ( type == 1 ) {
+		if ( type == 0 ) {
+			f3 dnew = fr.normal+unitV( s ) ;
+			if ( fabsf( dnew.x )<1e-8f && fabsf( dnew.y )<1e-8f && fabsf( dnew.z )<1e-8f )   // util.h:8 kNear0
+				dnew = fr.normal ;
+			out = dnew ;
+			return true ;
+		}
 		const f3 r = reflect( unitV( dir ), fr.normal ) ;
-		out = r+RTX_LDG( &ts->fuzz )*rng.rndVin1sphere() ;
-		attened = mk3( RTX_LDG( ts->albedo ), RTX_LDG( ts->albedo+1 ), RTX_LDG( ts->albedo+2 ) ) ;
+		out = r+RTX_LDG( &ts->fuzz )*s ;
 		return dot( out, fr.normal )>0.f ;
 	}
 	const f3 d1V = unitV( dir ) ;

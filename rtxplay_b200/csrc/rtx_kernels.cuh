@@ -142,14 +142,21 @@ inline void unit_plan( FrameArgs& a ) {
 	a.taper_s0[n] = uint16_t( s ) ;
 	a.chunks_taper = n ;
 }
+#if defined( RTX_MAXNREG )
+#define RTX_RENDER_BOUNDS __maxnreg__( RTX_MAXNREG )                 // (tuning: an exact register budget instead of a CTA count)
+#else
+#define RTX_RENDER_BOUNDS __launch_bounds__( 32, RTX_MIN_CTAS )
+#endif
 template <bool GUIDES>
-__global__ void __launch_bounds__( 32, RTX_MIN_CTAS ) k_render( const __grid_constant__ FrameArgs a, uint32_t* unit_counter, int32_t* ovf_all ) {
+__global__ void RTX_RENDER_BOUNDS k_render( const __grid_constant__ FrameArgs a, uint32_t* unit_counter, int32_t* ovf_all ) {
 	const uint32_t lane = threadIdx.x ;
 	const uint32_t lt = ( 1u<<lane )-1u ;
 #if defined( RTX_REGPOOL )
 	__shared__ uint32_t stack_words[2*RTX_POOL_STACK*32] ;
 	RegPool p ;
 	p.stk = uint32_t( __cvta_generic_to_shared( stack_words+lane ) ) ;
+	__shared__ uint32_t cold_words[( RTX_COLD_WORDS>0 ? RTX_COLD_WORDS : 1 )*32] ;
+	p.cold = uint32_t( __cvta_generic_to_shared( cold_words+lane ) ) ;
 	p.ovf = ovf_all+( size_t( blockIdx.x )*RTX_POOL_R+lane )*RTX_POOL_OVF*2 ;
 #else
 	__shared__ uint32_t words[F_WORDS*RTX_POOL_R] ;

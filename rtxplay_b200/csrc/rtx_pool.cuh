@@ -88,14 +88,45 @@ struct DevPool {
 // one ray per lane, state in registers (every field index is a compile-time constant), only
 // the stack in shared memory: no shared-memory traffic for the state, no limit on resident
 // warps from it, at the price of fewer candidate rays per vote (RTX_K must be 1)
+// Fields that are touched a few times per ray only can live in shared memory instead (a
+// lane-private column next to the stack, conflict free): RTX_COLD selects how many groups --
+//   1: path state (throughput, stream, pixel, counters) and the hit details (u, v, record, prim)
+//   2: + the world-space ray (read when a thing is entered or left, and by shading)
+//   3: + the low part of the object-space origin (read by leaf steps)
+// Every field index is a compile-time constant where it is used, so the choice folds away.
+#ifndef RTX_COLD
+#define RTX_COLD 0
+#endif
+__device__ __forceinline__ constexpr int cold_slot( int fld ) {
+	int n = 0 ;
+#if RTX_COLD >= 1
+	if ( fld>=F_THRX && fld<=F_META ) return n+fld-F_THRX ;
+	n += F_META-F_THRX+1 ;
+	if ( fld>=F_PRIM && fld<=F_TRIJ ) return n+fld-F_PRIM ;
+	n += F_TRIJ-F_PRIM+1 ;
+#endif
+#if RTX_COLD >= 2
+	if ( fld>=F_OX && fld<=F_DZ ) return n+fld-F_OX ;
+	n += F_DZ-F_OX+1 ;
+#endif
+#if RTX_COLD >= 3
+	if ( fld>=F_LX && fld<=F_LZ ) return n+fld-F_LX ;
+	n += F_LZ-F_LX+1 ;
+#endif
+	return fld<0 ? n : -1 ;   // cold_slot( -1 ) = number of cold fields
+}
+#define RTX_COLD_WORDS ( cold_slot( -1 ) )
 struct RegPool {
 	uint32_t  r[F_STACK] ;
 	uint32_t  stk ;    // shared-space byte address of this lane's stack column (entry i at stk + i*256: ref, +128: distance)
+	uint32_t  cold ;   // shared-space byte address of this lane's column of cold fields (field s at cold + s*128)
 	int32_t*  ovf ;    // this lane's overflow entries (pairs)
-	__device__ __forceinline__ float    f( int fld, int ) const { return __uint_as_float( r[fld] ) ; }
-	__device__ __forceinline__ int32_t  i( int fld, int ) const { return int32_t( r[fld] ) ; }
-	__device__ __forceinline__ void     sf( int fld, int, float v ) { r[fld] = __float_as_uint( v ) ; }
-	__device__ __forceinline__ void     si( int fld, int, int32_t v ) { r[fld] = uint32_t( v ) ; }
+	__device__ __forceinline__ uint32_t ldc( int s ) const { uint32_t v ; asm volatile( "ld.shared.u32 %0, [%1];" : "=r"( v ) : "r"( cold+uint32_t( s )*128u ) : "memory" ) ; return v ; }
+	__device__ __forceinline__ void     stc( int s, uint32_t v ) { asm volatile( "st.shared.u32 [%0], %1;" :: "r"( cold+uint32_t( s )*128u ), "r"( v ) : "memory" ) ; }
+	__device__ __forceinline__ float    f( int fld, int ) const { return __uint_as_float( cold_slot( fld )>=0 ? ldc( cold_slot( fld ) ) : r[fld] ) ; }
+	__device__ __forceinline__ int32_t  i( int fld, int ) const { return int32_t( cold_slot( fld )>=0 ? ldc( cold_slot( fld ) ) : r[fld] ) ; }
+	__device__ __forceinline__ void     sf( int fld, int, float v ) { if ( cold_slot( fld )>=0 ) stc( cold_slot( fld ), __float_as_uint( v ) ) ; else r[fld] = __float_as_uint( v ) ; }
+	__device__ __forceinline__ void     si( int fld, int, int32_t v ) { if ( cold_slot( fld )>=0 ) stc( cold_slot( fld ), uint32_t( v ) ) ; else r[fld] = uint32_t( v ) ; }
 	__device__ __forceinline__ void     push( int, int32_t& sp, int32_t v, float t ) {
 		if ( sp<RTX_POOL_STACK ) {
 			const uint32_t a = stk+uint32_t( sp )*256u ;
@@ -242,7 +273,7 @@ template <class P> RTX_HD int step_leaf( P& p, int slot, const SceneDev& S ) {
 	for ( uint32_t k = 0 ; k<count ; k++ ) {
 		RTX_COUNT( tris ) ;
 		const q4* T = tris+size_t( first+k )*RTX_TRI_RECS ;
-		const o8 t01 = ldo( T ), t23 = ldo( T+2 ) ;
+		const o8 t01 = ldo_tri( T ), t23 = ldo_tri( T+2 ) ;
 		const q4 a = t01.a, b = t01.b, c = t23.a ;
 		float t, u, v ;
 		if ( tri_test( mk3( a.x, a.y, a.z ), mk3( b.x, b.y, b.z ), mk3( c.x, c.y, c.z ), ohi, olo, dd, 1e-3f, t, u, v ) ) {

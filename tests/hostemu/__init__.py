@@ -22,7 +22,7 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 
 
-def render(things, cam, w, h, spp, depth=50, seed=4711, sample0=0, sample_stride=1, meshes=None, brute=False, pool=True):
+def render(things, cam, w, h, spp, depth=50, seed=4711, sample0=0, sample_stride=1, meshes=None, brute=False, pool=True, want_first=True):
     L = lib()
     things = np.ascontiguousarray(things, dtype=np.float64).reshape(-1, 20)
     cam = np.ascontiguousarray(cam, dtype=np.float64)
@@ -40,7 +40,7 @@ def render(things, cam, w, h, spp, depth=50, seed=4711, sample0=0, sample_stride
     ft = np.zeros((h, w), dtype=np.float32)
     L.emu_render(_p(things), ctypes.c_int(len(things)), ctypes.c_int(n), vp, _p(nv), ip, _p(nt), _p(cam),
                  ctypes.c_int(w), ctypes.c_int(h), ctypes.c_int(spp), ctypes.c_int(depth), ctypes.c_uint64(seed),
-                 ctypes.c_int(sample0), ctypes.c_int(sample_stride), _p(fix), _p(rpp), _p(fid), _p(ft),
+                 ctypes.c_int(sample0), ctypes.c_int(sample_stride), _p(fix), _p(rpp), _p(fid if want_first else None), _p(ft if want_first else None),
                  ctypes.c_int(1 if brute else 0), ctypes.c_int(1 if pool else 0))
     return dict(fix=fix, rpp=rpp, first_id=fid, first_t=ft)
 
@@ -76,3 +76,37 @@ def trace(things, cam, w, h, spp, depth=50, seed=4711, meshes=None):
         raise RuntimeError("trace larger than the buffer")
     return buf.raw[:got]
 
+
+
+def warpsim(things, cam, w, h, unit_spp=64, units_per_warp=16, tile_step=97, depth=50, seed=4711, meshes=None,
+            policy=0, sticky=5, t1=24, t2=33, costs=(12, 130, 40, 75, 60, 230, 150, 600, 200, 90)):
+    """Warp scheduling simulator (emu_warpsim in hostemu.cu): iterations / lane-steps per step
+    kind and a rough instruction estimate for the vote policy of k_render."""
+    L = lib()
+    things = np.ascontiguousarray(things, dtype=np.float64).reshape(-1, 20)
+    cam = np.ascontiguousarray(cam, dtype=np.float64)
+    meshes = meshes or []
+    v = [np.ascontiguousarray(m[0], dtype=np.float32).reshape(-1, 3) for m in meshes]
+    i = [np.ascontiguousarray(m[1], dtype=np.uint32).reshape(-1, 3) for m in meshes]
+    n = len(meshes)
+    vp = (ctypes.c_void_p * max(n, 1))(*[a.ctypes.data for a in v])
+    ip = (ctypes.c_void_p * max(n, 1))(*[a.ctypes.data for a in i])
+    nv = np.array([len(a) for a in v] or [0], dtype=np.uint32)
+    nt = np.array([len(a) for a in i] or [0], dtype=np.uint32)
+    out = np.zeros(24, dtype=np.float64)
+    c = np.array(costs, dtype=np.float64)
+    if policy == 2:
+        L.emu_warpsim_pool(_p(things), ctypes.c_int(len(things)), ctypes.c_int(n), vp, _p(nv), ip, _p(nt), _p(cam),
+                           ctypes.c_int(w), ctypes.c_int(h), ctypes.c_int(unit_spp), ctypes.c_int(units_per_warp), ctypes.c_int(tile_step),
+                           ctypes.c_int(depth), ctypes.c_uint64(seed), ctypes.c_int(t1), ctypes.c_int(sticky), _p(c), _p(out))
+    else:
+      L.emu_warpsim(_p(things), ctypes.c_int(len(things)), ctypes.c_int(n), vp, _p(nv), ip, _p(nt), _p(cam),
+                  ctypes.c_int(w), ctypes.c_int(h), ctypes.c_int(unit_spp), ctypes.c_int(units_per_warp), ctypes.c_int(tile_step),
+                  ctypes.c_int(depth), ctypes.c_uint64(seed), ctypes.c_int(policy), ctypes.c_int(sticky), ctypes.c_int(t1), ctypes.c_int(t2),
+                  _p(c), _p(out))
+    names = ["", "node", "leaf", "thing", "shade", "regen", "swap", "batch"]
+    r = {"rays": out[16], "paths": out[18], "cost": out[17], "cost_per_ray": out[17] / max(out[16], 1)}
+    for k in range(1, 8):
+        if out[k]:
+            r[names[k]] = (out[k] / out[16], out[8 + k] / out[k])   # iterations per ray, lanes per iteration
+    return r

@@ -337,6 +337,274 @@ long long emu_trace( const double* things, int n_things, int n_meshes, const flo
 	return n ;
 }
 
+// ---- warp scheduling simulator (development instrument): 32 lanes run the step functions in
+// lockstep under the vote policy of k_render (policy 0) or the parked-shading policy
+// (policy 1, rtx_kernels.cuh RTX_PARK), counting iterations, lane-steps and a rough
+// instruction cost per step kind.  Results are schedule independent, so only the counts matter.
+//   out[0..7]   iterations per kind (1 node, 2 leaf, 3 thing, 4 shade, 5 regen, 6 swap, 7 batch)
+//   out[8..15]  lane-steps per kind
+//   out[16]     rays, out[17] estimated warp instructions, out[18] paths
+namespace {
+struct SimLane { HostPool act, park ; int kind ; int pstate ; } ;   // pstate: 0 empty, 1 finished, 2 ready
+enum { S_SWAP = 6, S_BATCH = 7, S_WAIT = 8, S_NONE = 9 } ;
+struct SimCost { double vote, node, leaf0, leaf1, thing0, thing1, sky, shade, regen, swap ; } ;
+}
+long long emu_warpsim( const double* things, int n_things, int n_meshes, const float* const* vces, const uint32_t* nv, const uint32_t* const* ices, const uint32_t* nt,
+		const double* cam, int w, int h, int unit_spp, int units_per_warp, int tile_step, int depth, uint64_t seed,
+		int policy, int sticky, int t1, int t2, const double* costs, double* out ) {
+	EmuScene E ;
+	build_scene( E, things, n_things, n_meshes, vces, nv, ices, nt ) ;
+	CameraDev c ;
+	c.eye = mk3( float( cam[0] ), float( cam[1] ), float( cam[2] ) ) ; c.u = mk3( float( cam[3] ), float( cam[4] ), float( cam[5] ) ) ;
+	c.v = mk3( float( cam[6] ), float( cam[7] ), float( cam[8] ) ) ; c.hvec = mk3( float( cam[9] ), float( cam[10] ), float( cam[11] ) ) ;
+	c.wvec = mk3( float( cam[12] ), float( cam[13] ), float( cam[14] ) ) ; c.dvec = mk3( float( cam[15] ), float( cam[16] ), float( cam[17] ) ) ;
+	c.aperture = float( cam[18] ) ;
+	SimCost K ; memcpy( &K, costs, sizeof( K ) ) ;
+	for ( int k = 0 ; k<24 ; k++ ) out[k] = 0. ;
+	const int tiles_x = ( w+7 )/8, tiles_y = ( h+3 )/4, n_tiles = tiles_x*tiles_y ;
+	std::vector<SimLane> L( 32 ) ;
+	double cost = 0. ;
+	for ( int tile0 = 0 ; tile0<n_tiles ; tile0 += tile_step ) {
+		// this warp's stream of units: unit q = chunk q/4 of tile tile0 + q%4 (a 4-tile strip, like an SM's shared block)
+		int unit_next = 0 ; uint32_t unit_pos = 0, unit_left = 0, ux0 = 0, uy0 = 0, us0 = 0 ; bool exhausted = false ;
+		auto serve = [&]( HostPool& P, int& kind_out ) -> bool {   // next path of the stream into P; false: none left
+			while ( true ) {
+				if ( unit_left == 0 ) {
+					if ( unit_next>=units_per_warp ) { exhausted = true ; return false ; }
+					const int tile = ( tile0+unit_next%4 )%n_tiles, chunk = unit_next/4 ;
+					unit_next++ ;
+					ux0 = uint32_t( tile%tiles_x )*8u ; uy0 = uint32_t( tile/tiles_x )*4u ; us0 = uint32_t( chunk*unit_spp ) ;
+					unit_pos = 0 ; unit_left = 32u*uint32_t( unit_spp ) ;
+				}
+				const uint32_t idx = unit_pos++ ; unit_left-- ;
+				const uint32_t px = idx&31u, smp = us0+( idx>>5 ) ;
+				const uint32_t x = ux0+( px&7u ), y = uy0+( px>>3 ) ;
+				if ( x<uint32_t( w ) && y<uint32_t( h ) ) {
+					kind_out = step_regen( P, 0, E.S, c, x, y, uint32_t( w ), uint32_t( h ), uint32_t( w )*y+x, seed, smp, uint32_t( depth ) ) ;
+					out[18] += 1. ;
+					return true ;
+				}
+			}
+		} ;
+		for ( int l = 0 ; l<32 ; l++ ) { L[l].kind = policy != 1 ? K_REGEN : S_NONE ; L[l].pstate = 0 ; }
+		int drain_k = 0 ;
+		while ( true ) {
+			int cnt[10] = { 0 } ; int vk[32] ;
+			int n_fin = 0 ;
+			for ( int l = 0 ; l<32 ; l++ ) {
+				int k = L[l].kind ;
+				if ( policy == 1 ) {
+					if ( L[l].pstate == 1 || ( L[l].pstate == 0 && ! exhausted ) ) n_fin++ ;
+					if ( k == K_SHADE ) k = L[l].pstate != 1 ? S_SWAP : S_WAIT ;                    // active ray finished
+					else if ( k == S_NONE ) k = L[l].pstate == 2 ? S_SWAP : ( L[l].pstate == 1 || ! exhausted ) ? S_WAIT : K_DONE ;
+				}
+				vk[l] = k ; cnt[k]++ ;
+			}
+			int kind = K_DONE, best = 0 ;
+			for ( int k = 1 ; k<=S_SWAP ; k++ ) if ( cnt[k] && ( ( cnt[k]<<3 )|k )>best ) { best = ( cnt[k]<<3 )|k ; kind = k ; }
+			if ( policy == 1 && ( n_fin>=t1 || cnt[S_WAIT]>=t2 || ( kind == K_DONE && cnt[S_WAIT] ) ) ) kind = S_BATCH ;
+			if ( kind == K_DONE ) break ;
+			if ( policy == 3 ) {
+				// drain variant: after a run of node steps, every other kind with enough waiting lanes
+				// (t1: leaf / thing, t2: shade / regen) takes one step before the vote returns to nodes
+				if ( drain_k == 0 && kind != K_NODE ) drain_k = K_LEAF ;
+				if ( drain_k ) {
+					int pick = 0 ;
+					for ( int k = drain_k ; k<=K_REGEN ; k++ ) if ( cnt[k]>=( k<=K_THING ? t1 : t2 ) ) { pick = k ; break ; }
+					if ( pick ) { kind = pick ; drain_k = pick+1 ; } else drain_k = 0 ;
+					if ( drain_k>K_REGEN ) drain_k = 0 ;
+				}
+			}
+			cost += K.vote ;
+			switch ( kind ) {
+				case K_NODE:
+					while ( true ) {
+						int n = 0 ;
+						for ( int l = 0 ; l<32 ; l++ ) if ( L[l].kind == K_NODE ) { L[l].kind = step_node( L[l].act, 0, E.S ) ; n++ ; }
+						out[K_NODE] += 1. ; out[8+K_NODE] += n ; cost += K.node ;
+						int m = 0 ;
+						for ( int l = 0 ; l<32 ; l++ ) if ( L[l].kind == K_NODE ) m++ ;
+						if ( m<sticky ) break ;
+					}
+					break ;
+				case K_LEAF: {
+					int n = 0, mx = 0 ;
+					for ( int l = 0 ; l<32 ; l++ ) if ( L[l].kind == K_LEAF ) {
+						const int cn = int( ( uint32_t( ~L[l].act.i( F_CUR, 0 ) )&7u )+1u ) ; if ( cn>mx ) mx = cn ;
+						L[l].kind = step_leaf( L[l].act, 0, E.S ) ; n++ ;
+					}
+					out[K_LEAF] += 1. ; out[8+K_LEAF] += n ; cost += K.leaf0+K.leaf1*mx ;
+					break ;
+				}
+				case K_THING: {
+					int n = 0 ; bool entered = false ;
+					for ( int l = 0 ; l<32 ; l++ ) if ( L[l].kind == K_THING ) {
+						const unsigned long long before = g_stats.spheres ;
+						L[l].kind = step_thing( L[l].act, 0, E.S ) ; n++ ;
+						if ( g_stats.spheres == before ) entered = true ;
+					}
+					out[K_THING] += 1. ; out[8+K_THING] += n ; cost += entered ? K.thing1 : K.thing0 ;
+					break ;
+				}
+				case K_SHADE: {   // policy 0 only
+					int n = 0 ; bool hit = false ;
+					for ( int l = 0 ; l<32 ; l++ ) if ( L[l].kind == K_SHADE ) {
+						f3 col, gn, ga ; bool g ; uint32_t sg ;
+						if ( L[l].act.i( F_THING, 0 )>=0 ) hit = true ;
+						L[l].kind = step_shade( L[l].act, 0, E.S, col, g, gn, ga, sg ) ; n++ ; out[16] += 1. ;
+					}
+					out[K_SHADE] += 1. ; out[8+K_SHADE] += n ; cost += hit ? K.shade : K.sky ;
+					break ;
+				}
+				case K_REGEN: {   // policy 0 only
+					int n = 0 ;
+					for ( int l = 0 ; l<32 ; l++ ) if ( L[l].kind == K_REGEN ) {
+						int k2 ;
+						if ( serve( L[l].act, k2 ) ) L[l].kind = k2 ; else L[l].kind = K_DONE ;
+						n++ ;
+					}
+					out[K_REGEN] += 1. ; out[8+K_REGEN] += n ; cost += K.regen ;
+					break ;
+				}
+				case S_SWAP: {
+					int n = 0 ;
+					for ( int l = 0 ; l<32 ; l++ ) if ( vk[l] == S_SWAP ) {
+						n++ ;
+						const bool had = L[l].kind == K_SHADE ;
+						const int ps = L[l].pstate ;
+						std::swap( L[l].act, L[l].park ) ;
+						L[l].pstate = had ? 1 : 0 ;
+						L[l].kind = ps == 2 ? kind_of( L[l].act.i( F_CUR, 0 ), -1 ) : S_NONE ;
+					}
+					out[S_SWAP] += 1. ; out[8+S_SWAP] += n ; cost += K.swap ;
+					break ;
+				}
+				case S_BATCH: {
+					int n = 0 ; bool hit = false, regen = false ;
+					for ( int l = 0 ; l<32 ; l++ ) {
+						bool need = L[l].pstate == 0 ;
+						if ( L[l].pstate == 1 ) {
+							f3 col, gn, ga ; bool g ; uint32_t sg ;
+							if ( L[l].park.i( F_THING, 0 )>=0 ) hit = true ;
+							const int k2 = step_shade( L[l].park, 0, E.S, col, g, gn, ga, sg ) ; n++ ; out[16] += 1. ;
+							if ( k2 == K_REGEN ) { L[l].pstate = 0 ; need = true ; } else L[l].pstate = 2 ;
+						}
+						if ( need && ! exhausted ) {
+							int k2 ;
+							if ( serve( L[l].park, k2 ) ) { L[l].pstate = 2 ; regen = true ; }
+						}
+					}
+					out[S_BATCH] += 1. ; out[8+S_BATCH] += n ; cost += ( hit ? K.shade : K.sky )+( regen ? K.regen : 0. ) ;
+					break ;
+				}
+			}
+		}
+	}
+	out[17] = cost ;
+	return 0 ;
+}
+
+// policy 2 of the simulator: R rays per warp whose state any lane can pick up (state in shared
+// memory, compacted by kind before every step): each iteration takes up to 32 rays of the kind
+// most rays are in.  out[] as emu_warpsim.
+long long emu_warpsim_pool( const double* things, int n_things, int n_meshes, const float* const* vces, const uint32_t* nv, const uint32_t* const* ices, const uint32_t* nt,
+		const double* cam, int w, int h, int unit_spp, int units_per_warp, int tile_step, int depth, uint64_t seed,
+		int R, int sticky, const double* costs, double* out ) {
+	EmuScene E ;
+	build_scene( E, things, n_things, n_meshes, vces, nv, ices, nt ) ;
+	CameraDev c ;
+	c.eye = mk3( float( cam[0] ), float( cam[1] ), float( cam[2] ) ) ; c.u = mk3( float( cam[3] ), float( cam[4] ), float( cam[5] ) ) ;
+	c.v = mk3( float( cam[6] ), float( cam[7] ), float( cam[8] ) ) ; c.hvec = mk3( float( cam[9] ), float( cam[10] ), float( cam[11] ) ) ;
+	c.wvec = mk3( float( cam[12] ), float( cam[13] ), float( cam[14] ) ) ; c.dvec = mk3( float( cam[15] ), float( cam[16] ), float( cam[17] ) ) ;
+	c.aperture = float( cam[18] ) ;
+	SimCost K ; memcpy( &K, costs, sizeof( K ) ) ;
+	for ( int k = 0 ; k<24 ; k++ ) out[k] = 0. ;
+	const int tiles_x = ( w+7 )/8, tiles_y = ( h+3 )/4, n_tiles = tiles_x*tiles_y ;
+	std::vector<HostPool> P( R ) ; std::vector<int> kd( R ) ;
+	double cost = 0. ;
+	for ( int tile0 = 0 ; tile0<n_tiles ; tile0 += tile_step ) {
+		int unit_next = 0 ; uint32_t unit_pos = 0, unit_left = 0, ux0 = 0, uy0 = 0, us0 = 0 ;
+		auto serve = [&]( HostPool& Q, int& kind_out ) -> bool {
+			while ( true ) {
+				if ( unit_left == 0 ) {
+					if ( unit_next>=units_per_warp ) return false ;
+					const int tile = ( tile0+unit_next%4 )%n_tiles, chunk = unit_next/4 ;
+					unit_next++ ;
+					ux0 = uint32_t( tile%tiles_x )*8u ; uy0 = uint32_t( tile/tiles_x )*4u ; us0 = uint32_t( chunk*unit_spp ) ;
+					unit_pos = 0 ; unit_left = 32u*uint32_t( unit_spp ) ;
+				}
+				const uint32_t idx = unit_pos++ ; unit_left-- ;
+				const uint32_t px = idx&31u, smp = us0+( idx>>5 ) ;
+				const uint32_t x = ux0+( px&7u ), y = uy0+( px>>3 ) ;
+				if ( x<uint32_t( w ) && y<uint32_t( h ) ) {
+					kind_out = step_regen( Q, 0, E.S, c, x, y, uint32_t( w ), uint32_t( h ), uint32_t( w )*y+x, seed, smp, uint32_t( depth ) ) ;
+					out[18] += 1. ;
+					return true ;
+				}
+			}
+		} ;
+		for ( int r = 0 ; r<R ; r++ ) kd[r] = K_REGEN ;
+		int sel[32] ;
+		auto pick = [&]( int kind ) { int n = 0 ; for ( int r = 0 ; r<R && n<32 ; r++ ) if ( kd[r] == kind ) sel[n++] = r ; return n ; } ;
+		while ( true ) {
+			int cnt[8] = { 0 } ;
+			for ( int r = 0 ; r<R ; r++ ) cnt[kd[r]]++ ;
+			int kind = K_DONE, best = 0 ;
+			for ( int k = 1 ; k<=K_REGEN ; k++ ) { const int cc = cnt[k]>32 ? 32 : cnt[k] ; if ( cc && ( ( cc<<3 )|k )>best ) { best = ( cc<<3 )|k ; kind = k ; } }
+			if ( kind == K_DONE ) break ;
+			cost += K.vote ;
+			switch ( kind ) {
+				case K_NODE:
+					while ( true ) {
+						const int n = pick( K_NODE ) ;
+						for ( int q = 0 ; q<n ; q++ ) kd[sel[q]] = step_node( P[sel[q]], 0, E.S ) ;
+						out[K_NODE] += 1. ; out[8+K_NODE] += n ; cost += K.node ;
+						int m = 0 ;
+						for ( int r = 0 ; r<R ; r++ ) if ( kd[r] == K_NODE ) m++ ;
+						if ( m<sticky ) break ;
+					}
+					break ;
+				case K_LEAF: {
+					const int n = pick( K_LEAF ) ; int mx = 0 ;
+					for ( int q = 0 ; q<n ; q++ ) {
+						const int cn = int( ( uint32_t( ~P[sel[q]].i( F_CUR, 0 ) )&7u )+1u ) ; if ( cn>mx ) mx = cn ;
+						kd[sel[q]] = step_leaf( P[sel[q]], 0, E.S ) ;
+					}
+					out[K_LEAF] += 1. ; out[8+K_LEAF] += n ; cost += K.leaf0+K.leaf1*mx ;
+					break ;
+				}
+				case K_THING: {
+					const int n = pick( K_THING ) ; bool entered = false ;
+					for ( int q = 0 ; q<n ; q++ ) {
+						const unsigned long long before = g_stats.spheres ;
+						kd[sel[q]] = step_thing( P[sel[q]], 0, E.S ) ;
+						if ( g_stats.spheres == before ) entered = true ;
+					}
+					out[K_THING] += 1. ; out[8+K_THING] += n ; cost += entered ? K.thing1 : K.thing0 ;
+					break ;
+				}
+				case K_SHADE: {
+					const int n = pick( K_SHADE ) ; bool hit = false ;
+					for ( int q = 0 ; q<n ; q++ ) {
+						f3 col, gn, ga ; bool g ; uint32_t sg ;
+						if ( P[sel[q]].i( F_THING, 0 )>=0 ) hit = true ;
+						kd[sel[q]] = step_shade( P[sel[q]], 0, E.S, col, g, gn, ga, sg ) ; out[16] += 1. ;
+					}
+					out[K_SHADE] += 1. ; out[8+K_SHADE] += n ; cost += hit ? K.shade : K.sky ;
+					break ;
+				}
+				default: {
+					const int n = pick( K_REGEN ) ;
+					for ( int q = 0 ; q<n ; q++ ) { int k2 ; kd[sel[q]] = serve( P[sel[q]], k2 ) ? k2 : K_DONE ; }
+					out[K_REGEN] += 1. ; out[8+K_REGEN] += n ; cost += K.regen ;
+				}
+			}
+		}
+	}
+	out[17] = cost ;
+	return 0 ;
+}
+
 // traversal counters since the last reset: rays, nodes, leaves, tris, things, spheres, enters, pushes, max stack
 void emu_stats( unsigned long long* out, int reset ) {
 	const unsigned long long v[9] = { g_stats.rays, g_stats.nodes, g_stats.leaves, g_stats.tris, g_stats.things, g_stats.spheres, g_stats.enters, g_stats.pushes, g_stats.maxsp } ;

@@ -311,3 +311,30 @@ def test_build_stage_times_and_read_probe():
         assert gbs > 2000.0            # L2-resident: far above anything a host path could show
     finally:
         ctx.close()
+
+
+def test_counted_traversal_work_equals_host_harness(spheres):
+    """The instrumented build (librtx_count.so, bench.py's "counted" leg) counts exactly the
+    traversal events the same step functions produce when the host harness runs them serially:
+    a ray's work does not depend on the schedule.  Child process: the library is chosen at load."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from tests import hostemu
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "rtxplay_b200", "librtx_count.so")
+    assert os.path.exists(lib), "librtx_count.so is not built (make -C rtxplay_b200/csrc)"
+    w, h, spp, ndiv = 120, 80, 2, 3
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--count-worker", "--width", str(w), "--height", str(h),
+                          "--count-spp", str(spp), "--ndiv", str(ndiv)], env=dict(os.environ, RTX_LIB=lib), capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    c = json.loads([l for l in out.stdout.splitlines() if l.startswith("COUNTED ")][-1][8:])
+    tab, meshes = scenes.table(spheres, "mesh", ndiv)
+    hostemu.stats()
+    e = hostemu.render(tab, api.camera_table(api.camera(aspratio=w / h)), w, h, spp, 50, meshes=meshes, pool=True, want_first=False)
+    s = hostemu.stats()
+    assert c["segments"] == int(e["rpp"].sum())
+    assert c["rays"] == c["segments"] == s["rays"]
+    for k_dev, k_host in (("nodes", "nodes"), ("leaves", "leaves"), ("tris", "tris"), ("things", "things"), ("culled_or_sphere_tests", "spheres")):
+        assert c[k_dev] == s[k_host], (k_dev, c[k_dev], s[k_host])

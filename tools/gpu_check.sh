@@ -13,7 +13,7 @@ d=json.loads(open('gpurun_out/bench_$tag.json').read().strip().splitlines()[-1])
 print('BENCH $tag: %.3f Gseg/s  %.1f ms/frame  e2e %.1f ms  kernel %.1f ms  launches %d  clocks %s' % (d['value']/1e9, d['ms_per_step'], d['e2e']['ms_per_frame'], d['roofline']['kernel_ms'], d['gpu_launches'], d['clocks']))
 PY
 if [ "${3:-prof}" = "prof" ]; then
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_render -s 1 -c 1 -o gpurun_out/prof_$tag -f python bench.py --steps 1 --warmup 1 --spp 8 --no-cpu > gpurun_out/ncu_full_$tag.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_render -s 1 -c 1 -o gpurun_out/prof_$tag -f python bench.py --steps 1 --warmup 1 --spp 8 --no-cpu --no-count > gpurun_out/ncu_full_$tag.log 2>&1
   ncu -i gpurun_out/prof_$tag.ncu-rep --page raw --csv > gpurun_out/prof_${tag}_raw.csv 2>/dev/null
   python - <<PY
 import csv

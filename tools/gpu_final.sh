@@ -7,11 +7,11 @@ o=gpurun_out
 (timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5) | tee $o/${tag}_pytest.log
 timeout 600 python bench.py > $o/${tag}_bench.json 2> $o/${tag}_bench.err; tail -c 300 $o/${tag}_bench.err
 timeout 600 python bench.py --impl reference > $o/${tag}_bench_reference.json 2> $o/${tag}_bench_reference.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $o/${tag}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu > $o/${tag}_launches.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_render -s 1 -c 1 -o $o/${tag}_k_render -f python bench.py --steps 1 --warmup 1 --spp 32 --no-cpu > $o/${tag}_ncu_full.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $o/${tag}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-count > $o/${tag}_launches.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_render -s 1 -c 1 -o $o/${tag}_k_render -f python bench.py --steps 1 --warmup 1 --spp 32 --no-cpu --no-count > $o/${tag}_ncu_full.log 2>&1
 ncu -i $o/${tag}_k_render.ncu-rep --page raw --csv > $o/${tag}_k_render_raw.csv 2>/dev/null
 ncu -i $o/${tag}_k_render.ncu-rep --page source --csv > $o/${tag}_k_render_source.csv 2>/dev/null
-timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum,l1tex__t_bytes.sum,gpu__time_duration.sum --clock-control none -k regex:k_render -s 1 -c 1 --csv --log-file $o/${tag}_k_render_traffic.csv python bench.py --steps 1 --warmup 1 --no-cpu > $o/${tag}_traffic.log 2>&1
+timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum,l1tex__t_bytes.sum,gpu__time_duration.sum --clock-control none -k regex:k_render -s 1 -c 1 --csv --log-file $o/${tag}_k_render_traffic.csv python bench.py --steps 1 --warmup 1 --no-cpu --no-count > $o/${tag}_traffic.log 2>&1
 python - <<PY
 import json
 for t in ("bench","bench_reference"):

@@ -2,7 +2,7 @@
 # usage: tools/gpu_prof.sh <tag> <lib> <carveout> [spp]  -- one ncu --set full capture of k_render
 tag=$1; lib=$2; carve=$3; spp=${4:-8}
 export RTX_LIB=$PWD/rtxplay_b200/$lib RTX_CARVEOUT=$carve
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_render -s 1 -c 1 -o gpurun_out/prof_$tag -f python bench.py --steps 1 --warmup 1 --spp $spp --no-cpu > gpurun_out/ncu_full_$tag.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_render -s 1 -c 1 -o gpurun_out/prof_$tag -f python bench.py --steps 1 --warmup 1 --spp $spp --no-cpu --no-count > gpurun_out/ncu_full_$tag.log 2>&1
 ncu -i gpurun_out/prof_$tag.ncu-rep --page raw --csv > gpurun_out/prof_${tag}_raw.csv 2>/dev/null
 python - <<PY
 import csv

@@ -2,7 +2,7 @@
 # usage: tools/gpu_sweep.sh "<lib>:<carveout> ..."   -- short bench of experimental builds
 for cfg in $1; do
   lib=${cfg%%:*}; carve=${cfg##*:}
-  RTX_LIB=$PWD/rtxplay_b200/$lib RTX_CARVEOUT=$carve timeout 300 python bench.py --steps 2 --warmup 1 --no-cpu ${2:-} > gpurun_out/sweep_tmp.json 2> gpurun_out/sweep_tmp.err
+  RTX_LIB=$PWD/rtxplay_b200/$lib RTX_CARVEOUT=$carve timeout 300 python bench.py --steps 2 --warmup 1 --no-cpu --no-count ${2:-} > gpurun_out/sweep_tmp.json 2> gpurun_out/sweep_tmp.err
   python - <<PY
 import json
 try:
