@@ -159,7 +159,7 @@ struct q4 { float x, y, z, w ; } ;   // 16-byte record, bit-compatible with floa
 #define RTX_TRI_RECS   4            // a triangle: (a, prim id) (e1, b.x) (e2, b.y) (b.z, c) = 64 bytes, two 256-bit loads
 #define RTX_WIDTH      4
 #ifndef RTX_LEAF_MAX
-#define RTX_LEAF_MAX   4            // triangles per mesh leaf, at most 8 (top level: 1 thing per leaf)
+#define RTX_LEAF_MAX   3            // triangles per mesh leaf, at most 8 (top level: 1 thing per leaf); measured 2/3/4/6/8: 708/684/698/690/697 ms
 #endif
 #define RTX_REF_EMPTY  0x7ffffffd
 #define RTX_STK_DONE   0x7ffffffe   // bottom of the stack
