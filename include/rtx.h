@@ -52,7 +52,18 @@ typedef struct {
 	uint32_t   accumulate ;     /* 0: start from zero (optx/camera_i.cu:52); 1: add to the buffers */
 	uint32_t   guides ;         /* 1: also fill the denoiser guide layers normals / albedos (optx/camera_i.cu:56-57,
 	                               99-101, 109-113; optx/optics_i.cu:97-101, 185-189) */
+	uint32_t   variant ;        /* RTX_VARIANT_*: which of the reference's programs the path semantics follow */
 } rtx_params ;
+
+/* The reference's own variants disagree in four places (SURVEY.md 8a "divergences").  RTOW is the
+ * CPU path rtow.cxx, the parity target and the default: pixel -> viewport over w-1 / h-1
+ * (rtow.cxx:112-113), Lambert with the near-zero guard (optics.h:17-18), `depth` scatter events and
+ * black when they are used up (rtow.cxx:39-42).  RTWO_I is the default OptiX build (iterative
+ * programs): over w / h (optx/camera_i.cu:61-62), no guard (optx/optics_i.cu:86), at most `depth`
+ * rays per path, and a path whose last ray still scattered keeps its throughput product as colour
+ * (optx/camera_i.cu:75-95).  RTWO_R is the -DRECURSIVE build: over w / h (optx/camera_r.cu:69-70),
+ * no guard (optx/optics_r.cu:108), black at the `depth`-th hit (optx/optics_r.cu:30-42). */
+enum { RTX_VARIANT_RTOW = 0, RTX_VARIANT_RTWO_I = 1, RTX_VARIANT_RTWO_R = 2 } ;
 
 typedef struct {
 	uint64_t segments ;         /* closest-hit queries of the last render (sum of RPP, optx/rtwo.cxx:588) */

@@ -87,9 +87,12 @@ class _Meshes:
 
 
 def render(kind, things, cam, w, h, spp, depth=50, seed=4711, sample0=0, sample_stride=1,
-           y0=0, y1=None, threads=0, meshes=None, want_first=False, want_guides=False):
-    """Returns dict(sum=double[h,w,3], fix=uint64[h,w,3], rpp=uint32[h,w], first_id, first_t)."""
+           y0=0, y1=None, threads=0, meshes=None, want_first=False, want_guides=False, variant=0):
+    """Returns dict(sum=double[h,w,3], fix=uint64[h,w,3], rpp=uint32[h,w], first_id, first_t).
+    variant: 0 rtow.cxx semantics (the parity target), 1 / 2 the iterative / recursive OptiX
+    programs where they differ (oracle.cxx Tracer::variant)."""
     L = lib()
+    L.orc_set_variant(ctypes.c_int(variant))
     y1 = h if y1 is None else y1
     things = np.ascontiguousarray(things, dtype=np.float64).reshape(-1, TH_STRIDE)
     cam = np.ascontiguousarray(cam, dtype=np.float64)
@@ -105,6 +108,7 @@ def render(kind, things, cam, w, h, spp, depth=50, seed=4711, sample0=0, sample_
                       ctypes.c_uint64(seed), ctypes.c_int(sample0), ctypes.c_int(sample_stride),
                       ctypes.c_int(y0), ctypes.c_int(y1), ctypes.c_int(threads),
                       _p(out["sum"]), _p(out["fix"]), _p(out["rpp"]), _p(fid), _p(ft), _p(gd))
+    L.orc_set_variant(ctypes.c_int(0))
     if rc != 0:
         raise RuntimeError("orc_render failed: %d" % rc)
     out["first_id"], out["first_t"], out["guide"] = fid, ft, gd

@@ -411,10 +411,15 @@ template <class R, class Rng> struct Tracer {
 	static float  pow5( float m )  { const float m2 = m*m ; return ( m2*m2 )*m ; }
 
 	// optics.h:15-24, 34-40, 51-68
+	// variant: which of the reference's programs the path follows where they disagree:
+	//   0 rtow.cxx (the parity target)   1 optx iterative programs (camera_i.cu, optics_i.cu)
+	//   2 optx recursive programs (camera_r.cu, optics_r.cu)
+	int variant = 0 ;
 	bool scatter( const ThingT<R>& th, const V3<R>& dir, const Hit<R>& h, V3<R>& attened, V3<R>& out ) {
 		if ( th.type == 0 ) {
 			V3<R> d = h.normal+rndVon1sphere() ;
-			if ( std::fabs( d.x )<Consts<R>::near0() && std::fabs( d.y )<Consts<R>::near0() && std::fabs( d.z )<Consts<R>::near0() )
+			// optics.h:17-18; optx/optics_i.cu:86 and optx/optics_r.cu:108 have no guard
+			if ( variant == 0 && std::fabs( d.x )<Consts<R>::near0() && std::fabs( d.y )<Consts<R>::near0() && std::fabs( d.z )<Consts<R>::near0() )
 				d = h.normal ;
 			out = d ; attened = th.albedo ;
 			return true ;
@@ -450,6 +455,9 @@ template <class R, class Rng> struct Tracer {
 		guide_set_ = false ;
 		std::vector<V3<R>>& att = att_ ;
 		att.clear() ;
+		// rtow.cxx:39-42 allows `depth` scatter events and tests before it intersects; the OptiX
+		// programs count rays: the depth-th hit is the last (optx/camera_i.cu:75-92, optx/optics_r.cu:30-42)
+		if ( variant != 0 ) depth = depth>1 ? depth-1 : 0 ;
 		V3<R> tail ;
 		bool first = true ;
 		while ( true ) {
@@ -469,9 +477,17 @@ template <class R, class Rng> struct Tracer {
 			}
 			if ( shot ) {
 				V3<R> attened, out ;
-				const bool go = depth>0 && scatter( scene->things[h.thing], dir, h, attened, out ) ;
-				if ( depth>0 && ! guide_set_ && scene->things[h.thing].type != 2 ) {
+				// (the iterative programs run the hit program of the last ray too)
+				const bool shaded = depth>0 || variant == 1 ;
+				const bool go = shaded && scatter( scene->things[h.thing], dir, h, attened, out ) ;
+				if ( shaded && ! guide_set_ && scene->things[h.thing].type != 2 ) {
 					guide_set_ = true ; guide_n_ = h.normal ; guide_a_ = scene->things[h.thing].albedo ;
+				}
+				if ( go && depth == 0 ) {
+					// optx/camera_i.cu:92-95: the loop ends with stat CONT, the throughput product is the colour
+					att.push_back( attened ) ;
+					tail = mk<R>( R( 1 ), R( 1 ), R( 1 ) ) ;
+					break ;
 				}
 				if ( go ) {
 					att.push_back( attened ) ;
@@ -515,6 +531,7 @@ struct RenderArgs {
 	int y0, y1 ;                     // rows [y0,y1)
 	int threads ;
 	int back_to_front ;
+	int variant ;                    // see Tracer::variant
 	double*   sum ;                  // [h*w*3] double sums (f64 kinds) or nullptr
 	uint64_t* fix ;                  // [h*w*3] fixed-point sums or nullptr
 	uint32_t* rpp ;                  // [h*w] segments per pixel or nullptr
@@ -529,6 +546,9 @@ template <class R, class Rng> void render_rows( const SceneT<R>& scene, const do
 	Tracer<R, Rng> tr ;
 	tr.scene = &scene ;
 	tr.setcam( cam ) ;
+	tr.variant = a.variant ;
+	// rtow.cxx:112-113 divides by w-1, h-1; optx/camera_i.cu:61-62 and optx/camera_r.cu:69-70 by w, h
+	const int wdiv = a.variant == 0 ? a.w-1 : a.w, hdiv = a.variant == 0 ? a.h-1 : a.h ;
 	for ( int y = yb-1 ; y>=ya ; --y ) {
 		for ( int x = 0 ; x<a.w ; ++x ) {
 			const size_t pix = size_t( a.w )*y+x ;
@@ -540,8 +560,8 @@ template <class R, class Rng> void render_rows( const SceneT<R>& scene, const do
 				const uint32_t sample = uint32_t( a.sample0+k*a.sample_stride ) ;
 				tr.rng.seed( a.seed, uint32_t( pix ), sample ) ;
 				// rtow.cxx:112-113
-				const R s = R( 2 )*( R( x )+tr.rnd() )/R( a.w-1 )-R( 1 ) ;
-				const R t = R( 2 )*( R( y )+tr.rnd() )/R( a.h-1 )-R( 1 ) ;
+				const R s = R( 2 )*( R( x )+tr.rnd() )/R( wdiv )-R( 1 ) ;
+				const R t = R( 2 )*( R( y )+tr.rnd() )/R( hdiv )-R( 1 ) ;
 				V3<R> ori, dir ;
 				tr.camray( s, t, ori, dir ) ;
 				int ft = -1, fp = -1 ; R ftt = R( -1 ) ;
@@ -686,6 +706,10 @@ void     orc_libc_reset( uint64_t skip ) {
 }
 
 // meshes: nm entries; vces[q] -> float[3*nv[q]], ices[q] -> uint32[3*nt[q]]
+// variant of the following orc_render calls (see Tracer::variant); 0 = rtow.cxx
+static int g_variant = 0 ;
+void orc_set_variant( int v ) { g_variant = v ; }
+
 int orc_render( int kind, const double* things, int n_things,
 		int n_meshes, const float* const* vces, const uint32_t* nv, const uint32_t* const* ices, const uint32_t* nt,
 		const double* cam, int w, int h, int spp, int depth, uint64_t seed, int sample0, int sample_stride,
@@ -695,7 +719,7 @@ int orc_render( int kind, const double* things, int n_things,
 	for ( int q = 0 ; q<n_meshes ; q++ ) { m[q].vces = vces[q] ; m[q].nv = nv[q] ; m[q].ices = ices[q] ; m[q].nt = nt[q] ; }
 	RenderArgs a ;
 	a.w = w ; a.h = h ; a.spp = spp ; a.depth = depth ; a.seed = seed ; a.sample0 = sample0 ; a.sample_stride = sample_stride ;
-	a.y0 = y0 ; a.y1 = y1 ; a.threads = threads ;
+	a.y0 = y0 ; a.y1 = y1 ; a.threads = threads ; a.variant = g_variant ;
 	a.sum = sum ; a.fix = fix ; a.rpp = rpp ; a.first_id = first_id ; a.first_t = first_t ; a.guide = guide ;
 	switch ( kind ) {
 		case ORC_F64_LIBC: a.back_to_front = 1 ; render<double, RngLibc>( things, n_things, m.data(), n_meshes, cam, a, false ) ; break ;

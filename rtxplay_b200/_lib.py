@@ -23,7 +23,7 @@ class RtxParams(ctypes.Structure):
     _fields_ = [("image_w", ctypes.c_uint32), ("image_h", ctypes.c_uint32), ("spp", ctypes.c_uint32),
                 ("depth", ctypes.c_uint32), ("camera", RtxCamera), ("seed", ctypes.c_uint64),
                 ("sample0", ctypes.c_uint32), ("sample_stride", ctypes.c_uint32), ("accumulate", ctypes.c_uint32),
-                ("guides", ctypes.c_uint32)]
+                ("guides", ctypes.c_uint32), ("variant", ctypes.c_uint32)]
 
 
 class RtxStats(ctypes.Structure):

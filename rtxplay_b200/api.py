@@ -14,6 +14,7 @@ from ._lib import RtxCamera, RtxOptics, RtxParams, RtxStats
 DIFFUSE, REFLECT, REFRACT = 0, 1, 2
 BUF_ACCUM, BUF_RAWRGB, BUF_RPP, BUF_IMAGE, BUF_HIT_ID, BUF_HIT_T, BUF_NORMALS, BUF_ALBEDOS, BUF_PICK_ID, BUF_GUIDE_ACC = range(10)
 PP_NONE, PP_SRGB = 0, 1
+VARIANT_RTOW, VARIANT_RTWO_I, VARIANT_RTWO_R = 0, 1, 2   # include/rtx.h RTX_VARIANT_*
 
 
 class RtxError(RuntimeError):
@@ -128,12 +129,12 @@ class Context:
         self._ck(self._L.rtx_resize(self._c, ctypes.c_uint32(w), ctypes.c_uint32(h)))
         self.w, self.h = w, h
 
-    def params(self, cam, spp, depth=50, seed=4711, sample0=0, sample_stride=1, accumulate=0, guides=0):
+    def params(self, cam, spp, depth=50, seed=4711, sample0=0, sample_stride=1, accumulate=0, guides=0, variant=0):
         p = RtxParams()
         p.image_w, p.image_h, p.spp, p.depth = self.w, self.h, spp, depth
         p.camera = cam
         p.seed, p.sample0, p.sample_stride, p.accumulate = seed, sample0, sample_stride, accumulate
-        p.guides = guides
+        p.guides, p.variant = guides, variant
         return p
 
     def render(self, p):

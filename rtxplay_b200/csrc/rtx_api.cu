@@ -358,13 +358,17 @@ CameraDev camera_dev( const rtx_camera& k ) {
 	return d ;
 }
 
+static_assert( int( RTX_VARIANT_RTOW ) == int( RTX_SEM_RTOW ) && int( RTX_VARIANT_RTWO_I ) == int( RTX_SEM_RTWO_I ) && int( RTX_VARIANT_RTWO_R ) == int( RTX_SEM_RTWO_R ), "variant codes" ) ;
+static_assert( sizeof( rtx_params ) == 128, "rtx_params layout (tests/test_abi_and_host.py)" ) ;
+
 FrameArgs frame_args( rtx_ctx* c, const rtx_params* p ) {
 	if ( ! c->built ) throw std::runtime_error( "rtx: acceleration structure not built (call rtx_accel_build)" ) ;
 	if ( p->image_w != c->w || p->image_h != c->h || c->w == 0 ) throw std::runtime_error( "rtx: image size differs from the last rtx_resize" ) ;
 	if ( p->image_w<2 || p->image_h<2 ) throw std::runtime_error( "rtx: image must be at least 2x2" ) ;
 	FrameArgs a ;
 	memset( &a, 0, sizeof( a ) ) ;
-	a.S = scene_dev( c ) ; a.cam = camera_dev( p->camera ) ;
+	if ( p->variant>RTX_VARIANT_RTWO_R ) throw std::runtime_error( "rtx: unknown variant" ) ;
+	a.S = scene_dev( c ) ; a.S.variant = p->variant ; a.cam = camera_dev( p->camera ) ;
 	a.w = p->image_w ; a.h = p->image_h ; a.spp = p->spp ; a.depth = p->depth ; a.seed = p->seed ;
 	a.sample0 = p->sample0 ; a.sample_stride = p->sample_stride ? p->sample_stride : 1u ; a.accumulate = p->accumulate ;
 	a.accum = c->d_accum ; a.hit_id = c->d_hit_id ; a.hit_t = c->d_hit_t ;

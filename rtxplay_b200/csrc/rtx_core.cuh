@@ -188,6 +188,16 @@ struct ThingShade {
 	const uint32_t* ices ;
 } ;
 
+// Which of the reference's own programs the path semantics follow (SURVEY.md 8a "divergences"):
+//   RTOW    rtow.cxx, the CPU path and the parity target: pixel -> viewport over w-1 / h-1, Lambert with
+//           the near-zero guard, `depth` scatter events and black when they are used up
+//   RTWO_I  the iterative OptiX programs (optx/camera_i.cu:59-95, optx/optics_i.cu:86): over w / h, no
+//           guard, at most `depth` rays per path, and a path whose last ray still scattered keeps its
+//           throughput product as colour
+//   RTWO_R  the recursive ones (optx/camera_r.cu:67-70, optx/optics_r.cu:30-42, :108): over w / h, no
+//           guard, black at the `depth`-th hit
+enum { RTX_SEM_RTOW = 0, RTX_SEM_RTWO_I = 1, RTX_SEM_RTWO_R = 2 } ;
+
 struct SceneDev {
 	const q4*         tlas_nodes ;
 	const uint32_t*   tlas_order ;   // leaf slot -> thing id
@@ -195,6 +205,7 @@ struct SceneDev {
 	const ThingTrav*  trav ;
 	const ThingShade* shade ;
 	uint32_t          n_things ;
+	uint32_t          variant ;      // RTX_SEM_* of the frame being rendered
 } ;
 
 struct CameraDev { f3 eye, u, v, hvec, wvec, dvec ; float aperture ; } ;
@@ -599,7 +610,7 @@ RTX_HD float schlick( float cos_theta, float ratio ) {                          
 
 // optics.h:15-24 (Diffuse), :34-40 (Reflect), :51-68 (Refract).  Returns false when
 // the path is absorbed.
-RTX_HD_CALL bool scatter( const ThingShade* ts, const f3& dir, const Frame& fr, Pcg& rng, f3& attened, f3& out ) {
+RTX_HD_CALL bool scatter( const ThingShade* ts, const f3& dir, const Frame& fr, Pcg& rng, f3& attened, f3& out, bool guard = true ) {
 	const int32_t type = RTX_LDG( &ts->type ) ;
 	if ( type != 2 ) {
 		// Diffuse and Reflect both start with one rndVin1sphere(): the lanes of a warp run that
@@ -609,7 +620,7 @@ RTX_HD_CALL bool scatter( const ThingShade* ts, const f3& dir, const Frame& fr, 
 		attened = mk3( RTX_LDG( ts->albedo ), RTX_LDG( ts->albedo+1 ), RTX_LDG( ts->albedo+2 ) ) ;
 		if ( type == 0 ) {
 			f3 dnew = fr.normal+unitV( s ) ;
-			if ( fabsf( dnew.x )<1e-8f && fabsf( dnew.y )<1e-8f && fabsf( dnew.z )<1e-8f )   // util.h:8 kNear0
+			if ( guard && fabsf( dnew.x )<1e-8f && fabsf( dnew.y )<1e-8f && fabsf( dnew.z )<1e-8f )   // util.h:8 kNear0 (optx/optics_i.cu:86 has no guard)
 				dnew = fr.normal ;
 			out = dnew ;
 			return true ;
@@ -640,9 +651,10 @@ RTX_HD f3 sky( const f3& dir ) {
 }
 
 // rtow.cxx:112-113 + camera.h:25-31
-RTX_HD_CALL void primary_ray( const CameraDev& cam, uint32_t x, uint32_t y, uint32_t w, uint32_t h, Pcg& rng, f3& ori, f3& dir ) {
-	const float s = 2.f*( float( x )+rng.rnd() )/float( w-1 )-1.f ;
-	const float t = 2.f*( float( y )+rng.rnd() )/float( h-1 )-1.f ;
+// (optx/camera_i.cu:61-62 divides by w and h: `whole`)
+RTX_HD_CALL void primary_ray( const CameraDev& cam, uint32_t x, uint32_t y, uint32_t w, uint32_t h, Pcg& rng, f3& ori, f3& dir, bool whole = false ) {
+	const float s = 2.f*( float( x )+rng.rnd() )/float( whole ? w : w-1 )-1.f ;
+	const float t = 2.f*( float( y )+rng.rnd() )/float( whole ? h : h-1 )-1.f ;
 	const f3 r = ( cam.aperture/2.f )*rng.rndVin1disk() ;
 	const f3 o = r.x*cam.u+r.y*cam.v ;
 	ori = cam.eye+o ;
@@ -652,26 +664,35 @@ RTX_HD_CALL void primary_ray( const CameraDev& cam, uint32_t x, uint32_t y, uint
 // a path colour channel in [0,1] -> 2^-32 fixed point (integer sums are associative)
 RTX_HD uint64_t tofix( float c ) { return uint64_t( c*4294967296.f ) ; }
 
+// scatter events a path may take before its next hit ends it: `depth` for rtow.cxx (rtow.cxx:39-42
+// tests before it intersects); the OptiX programs count rays, the depth-th hit is the last
+RTX_HD uint32_t sem_depth( uint32_t variant, uint32_t depth ) {
+	return variant == RTX_SEM_RTOW ? depth : ( depth>1u ? depth-1u : 0u ) ;
+}
+
 // One whole path (rtow.cxx:34-49 unrolled into a loop, throughput front to back).
 // Used by the host harness and the picker; the render kernel inlines the same steps
 // in its regenerating loop.
 template <class Stack>
 RTX_HD f3 path_radiance( const SceneDev& S, f3 ori, f3 dir, uint32_t depth, Pcg& rng, Stack& st, uint32_t& segments ) {
 	f3 thr = mk3( 1.f, 1.f, 1.f ) ;
+	depth = sem_depth( S.variant, depth ) ;
 	while ( true ) {
 		HitRec h ;
 		segments++ ;
 		closest( S, ori, dir, 1e-3f, st, h ) ;                       // util.h:9 kAcne0
 		if ( h.thing<0 )
 			return thr*sky( dir ) ;
-		if ( depth == 0 )
+		if ( depth == 0 && S.variant != RTX_SEM_RTWO_I )
 			return mk3( 0.f, 0.f, 0.f ) ;
 		Frame fr ;
 		frame_of( S, h, ori, dir, 1e-3f, fr ) ;
 		f3 att, out ;
-		if ( ! scatter( S.shade+h.thing, dir, fr, rng, att, out ) )
+		if ( ! scatter( S.shade+h.thing, dir, fr, rng, att, out, S.variant == RTX_SEM_RTOW ) )
 			return mk3( 0.f, 0.f, 0.f ) ;
 		thr = thr*att ;
+		if ( depth == 0 )
+			return thr ;                                             // optx/camera_i.cu:92-95
 		ori = fr.p ; dir = out ; depth-- ;
 	}
 }

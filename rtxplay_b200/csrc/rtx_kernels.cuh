@@ -367,7 +367,7 @@ __global__ void __launch_bounds__( RTX_BLOCK ) k_primary_hits( const FrameArgs a
 	Pcg rng ;
 	rng.seed( a.seed, pix, a.sample0 ) ;
 	f3 ori, dir ;
-	primary_ray( a.cam, x, y, a.w, a.h, rng, ori, dir ) ;
+	primary_ray( a.cam, x, y, a.w, a.h, rng, ori, dir, a.S.variant != RTX_SEM_RTOW ) ;
 	HitRec hit ;
 	closest( a.S, ori, dir, 1e-3f, st, hit, valid ) ;
 	if ( ! valid )
@@ -385,7 +385,7 @@ __global__ void k_pick( const FrameArgs a, uint32_t px, uint32_t py, uint32_t* p
 	Pcg rng ;
 	rng.seed( a.seed, a.w*py+px, a.sample0 ) ;
 	f3 ori, dir ;
-	primary_ray( a.cam, px, py, a.w, a.h, rng, ori, dir ) ;
+	primary_ray( a.cam, px, py, a.w, a.h, rng, ori, dir, a.S.variant != RTX_SEM_RTOW ) ;
 	HitRec hit ;
 	closest( a.S, ori, dir, 1e-3f, st, hit, threadIdx.x == 0 ) ;
 	if ( threadIdx.x == 0 )

@@ -364,14 +364,14 @@ template <class P> RTX_HD int step_shade( P& p, int slot, const SceneDev& S, f3&
 		c = thr*sky( dir ) ;
 		return K_REGEN ;
 	}
-	if ( depth_left == 0 )
+	if ( depth_left == 0 && S.variant != RTX_SEM_RTWO_I )
 		return K_REGEN ;
 	Frame fr ;
 	frame_of( S, h, ori, dir, 1e-3f, fr ) ;
 	Pcg rng ;
 	rng.state = uint64_t( uint32_t( p.i( F_RNG0, slot ) ) )|( uint64_t( uint32_t( p.i( F_RNG1, slot ) ) )<<32 ) ;
 	f3 att, out ;
-	const bool go = scatter( S.shade+h.thing, dir, fr, rng, att, out ) ;
+	const bool go = scatter( S.shade+h.thing, dir, fr, rng, att, out, S.variant == RTX_SEM_RTOW ) ;
 	uint32_t meta2 = meta ;
 	if ( ! ( meta&256u ) && RTX_LDG( &( S.shade+h.thing )->type ) != 2 ) {
 		guide = true ; gnormal = fr.normal ; galbedo = att ;   // att = the thing's albedo for diffuse / reflect
@@ -380,6 +380,10 @@ template <class P> RTX_HD int step_shade( P& p, int slot, const SceneDev& S, f3&
 	if ( ! go )
 		return K_REGEN ;
 	thr = thr*att ;
+	if ( depth_left == 0 ) {   // RTX_SEM_RTWO_I: the last ray scattered, its throughput is the colour (optx/camera_i.cu:92-95)
+		c = thr ;
+		return K_REGEN ;
+	}
 	st3( p, F_THRX, slot, thr ) ;
 	p.si( F_RNG0, slot, int32_t( uint32_t( rng.state ) ) ) ; p.si( F_RNG1, slot, int32_t( uint32_t( rng.state>>32 ) ) ) ;
 	p.si( F_META, slot, int32_t( meta2-1u ) ) ;
@@ -393,7 +397,8 @@ template <class P> RTX_HD int step_regen( P& p, int slot, const SceneDev& S, con
 	Pcg rng ;
 	rng.seed( seed, w*y+x, sample ) ;
 	f3 ori, dir ;
-	primary_ray( cam, x, y, w, h, rng, ori, dir ) ;
+	primary_ray( cam, x, y, w, h, rng, ori, dir, S.variant != RTX_SEM_RTOW ) ;
+	depth = sem_depth( S.variant, depth ) ;
 	st3( p, F_THRX, slot, mk3( 1.f, 1.f, 1.f ) ) ;
 	p.si( F_RNG0, slot, int32_t( uint32_t( rng.state ) ) ) ; p.si( F_RNG1, slot, int32_t( uint32_t( rng.state>>32 ) ) ) ;
 	p.si( F_PIX, slot, int32_t( tile_pixel ) ) ;

@@ -50,7 +50,7 @@ void Launcher::ignite( const CUstream& /*cuda_stream*/, bool once ) {
 	p.image_w = lp_general.image_w ; p.image_h = lp_general.image_h ;
 	p.spp = lp_general.spp ; p.depth = lp_general.depth ;
 	p.camera = lp_general.camera.derived() ;
-	p.seed = seed_ ; p.sample0 = 0 ; p.sample_stride = 1 ; p.accumulate = 0 ; p.guides = guides_ ? 1u : 0u ;
+	p.seed = seed_ ; p.sample0 = 0 ; p.sample_stride = 1 ; p.accumulate = 0 ; p.guides = guides_ ? 1u : 0u ; p.variant = variant_ ;
 
 	if ( once || lp_general.picker ) {
 		// scene editing: one primary ray, the thing id lands in *pick_id (device)

@@ -20,11 +20,16 @@ class Launcher {
 		void seed( unsigned long long seed ) { seed_ = seed ; }
 		// additive: fill lp_general.normals / albedos (the reference always does; here on request)
 		void guides( bool on ) { guides_ = on ; }
+		// additive: which of the reference's programs the paths follow where they disagree
+		// (include/rtx.h RTX_VARIANT_*): rtow.cxx by default, the iterative OptiX programs, or the
+		// recursive ones the reference selects at build time with -DRECURSIVE
+		void variant( unsigned int v ) { variant_ = v ; }
 
 	private:
 		rtx_ctx*           ctx_ ;
 		unsigned long long seed_ ;
 		bool               guides_ = false ;
+		unsigned int       variant_ = 0 ;
 
 		void bind() ;
 } ;

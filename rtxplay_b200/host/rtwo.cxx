@@ -181,6 +181,24 @@ int main( int argc, char* argv[] ) {
 		OptixShaderBindingTable sbt ;
 		Launcher launcher( pipeline, sbt ) ;
 		cg::launcher = &launcher ;
+		{
+			// path semantics where the reference's variants differ (include/rtx.h RTX_VARIANT_*): the
+			// reference picks its recursive programs at build time (-DRECURSIVE, optx/rtwo.cxx:44-50);
+			// here that macro, or RTWO_VARIANT=rtow|iterative|recursive at run time; default rtow.cxx
+#ifdef RECURSIVE
+			unsigned int variant = RTX_VARIANT_RTWO_R ;
+#else
+			unsigned int variant = RTX_VARIANT_RTOW ;
+#endif // RECURSIVE
+			if ( const char* e = getenv( "RTWO_VARIANT" ) ) {
+				const std::string v( e ) ;
+				if ( v == "rtow" ) variant = RTX_VARIANT_RTOW ;
+				else if ( v == "iterative" ) variant = RTX_VARIANT_RTWO_I ;
+				else if ( v == "recursive" ) variant = RTX_VARIANT_RTWO_R ;
+				else throw std::runtime_error( "RTWO_VARIANT must be rtow, iterative or recursive" ) ;
+			}
+			launcher.variant( variant ) ;
+		}
 		launcher.guides( args.param_D( Dns::NONE ) != Dns::NONE ) ;   // guide layers feed the denoiser / -G
 
 		// launch (the reference times ignite + stream destroy, optx/rtwo.cxx:542-546)

@@ -22,8 +22,9 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 
 
-def render(things, cam, w, h, spp, depth=50, seed=4711, sample0=0, sample_stride=1, meshes=None, brute=False, pool=True, want_first=True):
+def render(things, cam, w, h, spp, depth=50, seed=4711, sample0=0, sample_stride=1, meshes=None, brute=False, pool=True, want_first=True, variant=0):
     L = lib()
+    L.emu_set_variant(ctypes.c_int(variant))
     things = np.ascontiguousarray(things, dtype=np.float64).reshape(-1, 20)
     cam = np.ascontiguousarray(cam, dtype=np.float64)
     meshes = meshes or []
@@ -42,6 +43,7 @@ def render(things, cam, w, h, spp, depth=50, seed=4711, sample0=0, sample_stride
                  ctypes.c_int(w), ctypes.c_int(h), ctypes.c_int(spp), ctypes.c_int(depth), ctypes.c_uint64(seed),
                  ctypes.c_int(sample0), ctypes.c_int(sample_stride), _p(fix), _p(rpp), _p(fid if want_first else None), _p(ft if want_first else None),
                  ctypes.c_int(1 if brute else 0), ctypes.c_int(1 if pool else 0))
+    L.emu_set_variant(ctypes.c_int(0))
     return dict(fix=fix, rpp=rpp, first_id=fid, first_t=ft)
 
 

@@ -25,6 +25,8 @@ void trace_event( char c ) { if ( g_trace ) g_trace->push_back( c ) ; }
 
 namespace {
 
+uint32_t g_variant = 0 ;   // RTX_SEM_* of the following calls (emu_set_variant)
+
 struct HostStack {
 	int32_t v[256] ; int sp ;
 	RTX_HD void reset() { sp = 0 ; }
@@ -248,12 +250,14 @@ void build_scene( EmuScene& E, const double* things, int n_things, int n_meshes,
 	}
 	if ( n_things ) build_tree( plo, phi, E.tlas, 1 ) ;
 	E.S.tlas_nodes = E.tlas.nodes.data() ; E.S.tlas_order = E.tlas.order.data() ;
-	E.S.trav = E.trav.data() ; E.S.shade = E.shade.data() ; E.S.bsphere = E.bsphere.data() ; E.S.n_things = uint32_t( n_things ) ;
+	E.S.trav = E.trav.data() ; E.S.shade = E.shade.data() ; E.S.bsphere = E.bsphere.data() ; E.S.n_things = uint32_t( n_things ) ; E.S.variant = g_variant ;
 }
 
 } // namespace
 
 extern "C" {
+
+void emu_set_variant( int v ) { g_variant = uint32_t( v ) ; }
 
 // cam: 19 doubles (eye,u,v,hvec,wvec,dvec,aperture) as in the oracle tables
 int emu_render( const double* things, int n_things, int n_meshes, const float* const* vces, const uint32_t* nv, const uint32_t* const* ices, const uint32_t* nt,
@@ -275,7 +279,7 @@ int emu_render( const double* things, int n_things, int n_meshes, const float* c
 				Pcg rng ;
 				rng.seed( seed, pix, uint32_t( sample0+k*sample_stride ) ) ;
 				f3 ori, dir ;
-				primary_ray( c, uint32_t( x ), uint32_t( y ), uint32_t( w ), uint32_t( h ), rng, ori, dir ) ;
+				primary_ray( c, uint32_t( x ), uint32_t( y ), uint32_t( w ), uint32_t( h ), rng, ori, dir, g_variant != RTX_SEM_RTOW ) ;
 				if ( k == 0 && first_id ) {
 					HitRec hr ;
 					if ( brute ) closest_brute( E.S, ori, dir, 1e-3f, hr ) ;
@@ -315,7 +319,7 @@ long long emu_trace( const double* things, int n_things, int n_meshes, const flo
 				Pcg rng ;
 				rng.seed( seed, pix, uint32_t( k ) ) ;
 				f3 ori, dir ;
-				primary_ray( c, uint32_t( x ), uint32_t( y ), uint32_t( w ), uint32_t( h ), rng, ori, dir ) ;
+				primary_ray( c, uint32_t( x ), uint32_t( y ), uint32_t( w ), uint32_t( h ), rng, ori, dir, g_variant != RTX_SEM_RTOW ) ;
 				// path_radiance, with a ray separator
 				f3 thr = mk3( 1.f, 1.f, 1.f ) ; uint32_t dl = uint32_t( depth ) ;
 				while ( true ) {

@@ -37,7 +37,7 @@ def test_struct_sizes_match_header():
     # rtx_params: 4 u32 + camera (19 floats) + pad + u64 + 3 u32 (+pad)
     assert ctypes.sizeof(_lib.RtxCamera) == 19 * 4
     assert ctypes.sizeof(_lib.RtxOptics) == 24
-    assert ctypes.sizeof(_lib.RtxParams) == 120          # guides fills the former tail padding
+    assert ctypes.sizeof(_lib.RtxParams) == 128          # ... + guides, variant
     assert ctypes.sizeof(_lib.RtxStats) == 64
 
 
@@ -108,6 +108,34 @@ def test_cuda_core_on_host_equals_float_mirror(mode, ndiv, pool):
     assert np.array_equal(f["first_id"], e["first_id"])
     assert np.array_equal(f["rpp"], e["rpp"])
     assert np.array_equal(f["fix"], e["fix"])
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("mode,ndiv,depth", [("analytic", None, 50), ("mesh", 2, 3), ("analytic", None, 1)])
+def test_reference_variants_on_host(mode, ndiv, depth, variant):
+    """Where the reference's own programs disagree: the iterative (1) and recursive
+    (2) OptiX semantics -- pixel mapping over w / h, unguarded Lambert, rays instead of scatter events
+    counted, throughput kept / black at the limit -- in the CUDA core on the host == oracle<float>."""
+    sp = scenes.book1(seed=3)
+    tab, meshes = scenes.table(sp, mode, ndiv)
+    cam = api.camera_table(api.camera(aspratio=1.5))
+    w, h, spp = 60, 40, 2
+    f = orc.render(orc.F32_PCG, tab, cam, w, h, spp, depth, want_first=True, meshes=meshes, variant=variant)
+    f0 = orc.render(orc.F32_PCG, tab, cam, w, h, spp, depth, meshes=meshes)
+    assert not np.array_equal(f["fix"], f0["fix"])            # the variants do differ from rtow.cxx
+    for pool in (True, False):
+        e = hostemu.render(tab, cam, w, h, spp, depth, meshes=meshes, pool=pool, variant=variant)
+        assert np.array_equal(f["first_id"], e["first_id"])
+        assert np.array_equal(f["rpp"], e["rpp"])
+        assert np.array_equal(f["fix"], e["fix"])
+    assert int(f["rpp"].max()) <= depth * spp                  # the OptiX programs count rays
+    if depth == 1:
+        assert int(f["rpp"].sum()) == w * h * spp
+        # one ray per path: the recursive programs return black at the first hit, the iterative
+        # ones keep the throughput of that hit
+        r2 = orc.render(orc.F32_PCG, tab, cam, w, h, spp, depth, meshes=meshes, variant=2)
+        r1 = orc.render(orc.F32_PCG, tab, cam, w, h, spp, depth, meshes=meshes, variant=1)
+        assert int(r1["fix"].sum() >> 32) > int(r2["fix"].sum() >> 32)
 
 
 def test_general_affine_instances_on_host():

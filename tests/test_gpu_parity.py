@@ -38,6 +38,30 @@ def test_frame_equals_float_mirror(spheres, mode, ndiv, w, h, spp):
     ctx.close()
 
 
+@pytest.mark.parametrize("variant", [api.VARIANT_RTWO_I, api.VARIANT_RTWO_R])
+@pytest.mark.parametrize("mode,ndiv,depth", [("analytic", None, 50), ("mesh", 2, 4), ("mesh", 2, 1)])
+def test_reference_variants_equal_float_mirror(spheres, mode, ndiv, depth, variant):
+    """rtx_params.variant: the iterative / recursive OptiX semantics (include/rtx.h RTX_VARIANT_*)
+    through the render kernel, against the oracle's float mirror of the same variant, bit for bit --
+    radiance sums, segments, guide layers; primary-ray ids (pixel mapping over w / h)."""
+    ctx, tab, meshes = _ctx(spheres, mode, ndiv)
+    w, h, spp = 120, 80, 3
+    cam = api.camera(aspratio=w / h)
+    ctx.resize(w, h)
+    p = ctx.params(cam, spp, depth, guides=1, variant=variant)
+    ctx.render(p)
+    acc = ctx.read(api.BUF_ACCUM)
+    gacc = ctx.read(api.BUF_GUIDE_ACC)
+    ids, _ = ctx.primary_hits(p)
+    ref = orc.render(orc.F32_PCG, tab, api.camera_table(cam), w, h, spp, depth, want_first=True, want_guides=True, meshes=meshes, variant=variant)
+    assert np.array_equal(ids, ref["first_id"])
+    assert np.array_equal(acc[..., 3].astype(np.uint32), ref["rpp"])
+    assert np.array_equal(acc[..., :3], ref["fix"])
+    assert np.array_equal(gacc.reshape(h, w, 6), ref["guide"])
+    assert int(ref["rpp"].max()) <= depth * spp
+    ctx.close()
+
+
 def test_general_affine_instances():
     """Rotated / sheared / non-uniformly scaled mesh instances against the float mirror."""
     sp = scenes.affine_mix()
