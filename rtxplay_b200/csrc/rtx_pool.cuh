@@ -32,6 +32,9 @@ namespace rtx {
 #if RTX_K == 1 && ! defined( RTX_REGPOOL )
 #define RTX_REGPOOL 1
 #endif
+#ifndef RTX_PREFETCH
+#define RTX_PREFETCH 0          // L1 prefetches beyond the first line of the next leaf (bits: 1 its second line, 2 / 4 the second-nearest child when a leaf / a node)
+#endif
 #ifndef RTX_POOL_STACK
 #define RTX_POOL_STACK 16       // stack entries (work item + its entry distance) per slot kept in shared memory
 #endif
@@ -222,8 +225,14 @@ template <class P> RTX_HD int finish_step( P& p, int slot, int32_t cur, int32_t 
 		prefetch_line( ldp<P, q4>( p, F_NODES0, slot )+size_t( cur )*RTX_NODE_RECS ) ;
 	else
 #endif
-	if ( kind == K_LEAF )
-		prefetch_line( ldp<P, q4>( p, F_TRIS0, slot )+size_t( uint32_t( ~cur )>>3 )*RTX_TRI_RECS ) ;
+	if ( kind == K_LEAF ) {
+		const q4* T = ldp<P, q4>( p, F_TRIS0, slot )+size_t( uint32_t( ~cur )>>3 )*RTX_TRI_RECS ;
+		prefetch_line( T ) ;
+#if RTX_PREFETCH & 1
+		// a leaf of three 64-byte records spans two or three 128-byte lines
+		if ( ( uint32_t( ~cur )&7u )>=1u ) prefetch_line( T+2*RTX_TRI_RECS-1 ) ;
+#endif
+	}
 	return kind ;
 }
 
@@ -254,6 +263,19 @@ template <class P> RTX_HD int step_node( P& p, int slot, const SceneDev& S ) {
 		if ( t3<INFINITY ) p.push( slot, sp, c3, t3 ) ;
 		if ( t2<INFINITY ) p.push( slot, sp, c2, t2 ) ;
 		if ( t1<INFINITY ) p.push( slot, sp, c1, t1 ) ;
+#if RTX_PREFETCH & 2
+		// the second-nearest child, when it is a mesh leaf, is usually next but one: fetch its triangles now
+		if ( t1<INFINITY && c1<0 && level>=0 ) prefetch_line( ldp<P, q4>( p, F_TRIS0, slot )+size_t( uint32_t( ~c1 )>>3 )*RTX_TRI_RECS ) ;
+#endif
+#if RTX_PREFETCH & 8
+		// ... every pushed inner node into L2
+		if ( t1<INFINITY && c1>=0 ) asm volatile( "prefetch.global.L2 [%0];" :: "l"( ldp<P, q4>( p, F_NODES0, slot )+size_t( c1 )*RTX_NODE_RECS ) ) ;
+		if ( t2<INFINITY && c2>=0 ) asm volatile( "prefetch.global.L2 [%0];" :: "l"( ldp<P, q4>( p, F_NODES0, slot )+size_t( c2 )*RTX_NODE_RECS ) ) ;
+#endif
+#if RTX_PREFETCH & 4
+		// ... or an inner node: its line
+		if ( t1<INFINITY && c1>=0 ) prefetch_line( ldp<P, q4>( p, F_NODES0, slot )+size_t( c1 )*RTX_NODE_RECS ) ;
+#endif
 		cur = c0 ;
 	}
 	return finish_step( p, slot, cur, sp, level ) ;
