@@ -21,3 +21,16 @@ for t in ("bench","bench_reference"):
     except Exception as e: print(t,"FAILED",e)
 PY
 tail -3 $o/${tag}_k_render_traffic.csv
+# the other configurations of BASELINE.json, short runs without the CPU / counted legs
+for cfg in "analytic:--mode analytic" "spp1:--spp 1 --steps 20" "uhd64:--width 3840 --height 2160 --spp 64" "stress:--scene grid316 --spp 64" "counted_analytic:--mode analytic --steps 1 --warmup 1"; do
+  name=${cfg%%:*}; opts=${cfg#*:}
+  extra="--no-cpu --no-count"; [ "$name" = counted_analytic ] && extra="--no-cpu"
+  timeout 600 python bench.py $extra --steps 3 --warmup 3 $opts > $o/${tag}_bench_$name.json 2> $o/${tag}_bench_$name.err
+  python - <<PY
+import json
+try:
+    d=json.loads(open("$o/${tag}_bench_$name.json").read().strip().splitlines()[-1])
+    print("EXTRA $name: %.3f Gseg/s  %.2f ms/frame  build %s" % (d["value"]/1e9, d["ms_per_step"], {k: round(v,2) for k,v in d["config"]["build_ms"].items() if not isinstance(v, dict)}))
+except Exception as e: print("EXTRA $name FAILED", e)
+PY
+done
