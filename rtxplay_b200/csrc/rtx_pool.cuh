@@ -3,20 +3,21 @@
 // Why: traced rays need very different work -- inner nodes, triangle leaves, instance
 // entries, shading, new paths -- and a warp that binds one ray to one lane spends most of
 // its issue slots on a handful of lanes (measured on B200, ncu: 6.9 of 32 lanes active,
-// profiles/r01_v0_*).  Here every lane owns RTX_K ray slots whose state lives in shared
-// memory (SoA over slots: word f of slot s at [f*R+s], s = j*32+lane, so a lane only ever
-// touches bank `lane` -- conflict-free by construction).  Each iteration the warp votes
-// (ballot) for the step kind most lanes can take, and every lane advances ONE of its rays
-// of that kind by one step:
+// profiles/r01_v0_*).  Here a ray is always in one of five states, its whole state sits in
+// the registers of its lane (RegPool; only the traversal stack is a lane-private column of
+// shared memory), and each iteration the warp votes for the step kind most lanes can take;
+// the lanes in that state advance their ray by one step:
 //     NODE   test the four children of a wide BVH node, push / pop
 //     LEAF   test the 1..4 triangles of a mesh leaf
 //     THING  top-level leaf: analytic sphere test, or transform the ray into a mesh
 //     SHADE  ray finished: sky or scatter, start the next ray of the path
 //     REGEN  path finished: fetch the next (pixel, sample) of the warp's tile
-// Rays of other kinds wait in their slots; while a ray waits, the node it needs next has
-// already been prefetched.  Results do not depend on the schedule: closest hits are
-// order-independent (rtx_core.cuh better()), every path owns its random stream, and
-// radiance is summed in fixed point.
+// Rays of other kinds wait; while a ray waits for a leaf step, its triangles are being
+// prefetched.  Results do not depend on the schedule: closest hits are order-independent
+// (rtx_core.cuh better()), every path owns its random stream, and radiance is summed in
+// fixed point.  (RTX_K > 1 selects the measured alternative: RTX_K lane-private ray slots per
+// lane in shared memory, DevPool -- more candidates per vote, but 14-16 warps per SM and no L1:
+// 890-950 ms per frame against 678)
 //
 // The step functions are templated on the slot store so that the host harness can run the
 // very same code serially (tests/hostemu).
