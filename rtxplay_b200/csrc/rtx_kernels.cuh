@@ -271,7 +271,7 @@ __global__ void RTX_RENDER_BOUNDS k_render( const __grid_constant__ FrameArgs a,
 					if ( unit_left == 0 && ! exhausted ) {
 						uint32_t u = 0 ;
 #if RTX_SM_SUPER
-						// the warps of an SM share a block of 8x4 adjacent tiles (one chunk of samples): what one
+						// the warps of an SM share a block of 2x2 adjacent tiles x 8 sample chunks: what one
 						// warp pulls into L1 the others use.  Per-SM word: (block+1)<<32 | next tile of the block;
 						// the warp that draws the first index past the block fetches the SM's next block from the
 						// global counter, the others retry until it is installed.
