@@ -155,9 +155,11 @@ struct q4 { float x, y, z, w ; } ;   // 16-byte record, bit-compatible with floa
 // child ref: 0 <= ref < RTX_REF_EMPTY inner node index; ref < 0 leaf, ~ref = first<<3 |
 // (count-1); RTX_REF_EMPTY marks an unused slot, whose box is lo = hi = +inf (never entered).  The two values above it are stack
 // sentinels.
-#define RTX_NODE_RECS  8
+#ifndef RTX_WIDTH
+#define RTX_WIDTH      4            // children per node: 4, or 8 (experimental: two such 128-byte blocks per node, children 0-3 and 4-7)
+#endif
+#define RTX_NODE_RECS  ( 2*RTX_WIDTH )
 #define RTX_TRI_RECS   4            // a triangle: (a, prim id) (e1, b.x) (e2, b.y) (b.z, c) = 64 bytes, two 256-bit loads
-#define RTX_WIDTH      4
 #ifndef RTX_LEAF_MAX
 #define RTX_LEAF_MAX   3            // triangles per mesh leaf, at most 8 (top level: 1 thing per leaf); measured 2/3/4/6/8: 708/684/698/690/697 ms
 #endif
@@ -380,6 +382,46 @@ RTX_HD float slab( float lox, float loy, float loz, float hix, float hiy, float 
 	return tn<=tf*RTX_SLACK ? tn : INFINITY ;
 }
 
+#ifndef RTX_W8_ORDER
+#define RTX_W8_ORDER 0
+#endif
+#if RTX_WIDTH == 8
+// the eight (entry distance, child) pairs of a node, nearest first (misses: +inf, last)
+RTX_HD void node_children8( const q4* n, const f3& idir, const f3& ood, float tmin, float tbest_s, float t[8], int32_t c[8] ) {
+#pragma unroll
+	for ( int h = 0 ; h<2 ; h++ ) {
+		const o8 n01 = ldo( n+8*h ), n23 = ldo( n+8*h+2 ), n45 = ldo( n+8*h+4 ), n67 = ldo( n+8*h+6 ) ;
+		const q4 lx = n01.a, ly = n01.b, lz = n23.a, hx = n23.b, hy = n45.a, hz = n45.b, rf = n67.a ;
+		c[4*h] = asint( rf.x ) ; c[4*h+1] = asint( rf.y ) ; c[4*h+2] = asint( rf.z ) ; c[4*h+3] = asint( rf.w ) ;
+		t[4*h]   = slab( lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, idir, ood, tmin, tbest_s ) ;
+		t[4*h+1] = slab( lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, idir, ood, tmin, tbest_s ) ;
+		t[4*h+2] = slab( lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, idir, ood, tmin, tbest_s ) ;
+		t[4*h+3] = slab( lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, idir, ood, tmin, tbest_s ) ;
+	}
+#define RTX_CS( i, j ) if ( t[j]<t[i] ) { const float tt = t[i] ; t[i] = t[j] ; t[j] = tt ; const int32_t cc = c[i] ; c[i] = c[j] ; c[j] = cc ; }
+#if RTX_W8_ORDER == 1
+	// cheaper: each half sorted (5 comparators), then the half with the nearer first child in front
+	RTX_CS( 0, 1 ) RTX_CS( 2, 3 ) RTX_CS( 0, 2 ) RTX_CS( 1, 3 ) RTX_CS( 1, 2 )
+	RTX_CS( 4, 5 ) RTX_CS( 6, 7 ) RTX_CS( 4, 6 ) RTX_CS( 5, 7 ) RTX_CS( 5, 6 )
+	if ( t[4]<t[0] ) {
+#pragma unroll
+		for ( int k = 0 ; k<4 ; k++ ) { const float tt = t[k] ; t[k] = t[4+k] ; t[4+k] = tt ; const int32_t cc = c[k] ; c[k] = c[4+k] ; c[4+k] = cc ; }
+	}
+	// (callers push 7..1: a miss inside the front half must not hide the hits behind it)
+#else
+	// 19-comparator network for eight keys
+	RTX_CS( 0, 1 ) RTX_CS( 2, 3 ) RTX_CS( 4, 5 ) RTX_CS( 6, 7 )
+	RTX_CS( 0, 2 ) RTX_CS( 1, 3 ) RTX_CS( 4, 6 ) RTX_CS( 5, 7 )
+	RTX_CS( 1, 2 ) RTX_CS( 5, 6 ) RTX_CS( 0, 4 ) RTX_CS( 3, 7 )
+	RTX_CS( 1, 5 ) RTX_CS( 2, 6 )
+	RTX_CS( 1, 4 ) RTX_CS( 3, 6 )
+	RTX_CS( 2, 4 ) RTX_CS( 3, 5 )
+	RTX_CS( 3, 4 )
+#endif
+#undef RTX_CS
+}
+#endif
+
 // ----------------------------------------------------------------------------- traversal
 // "while-while" over the 4-wide trees, warp-synchronous: all lanes of the warp first walk
 // inner nodes until none of them holds one (lanes that reached a leaf wait), then every lane
@@ -415,6 +457,18 @@ RTX_HD void closest( const SceneDev& S, const f3& o, const f3& d, float tmin, St
 			if ( uint32_t( cur )<uint32_t( RTX_REF_EMPTY ) ) {
 				const q4* n = nodes+size_t( cur )*RTX_NODE_RECS ;
 				RTX_COUNT( nodes ) ; RTX_EVENT( 'N' ) ;
+#if RTX_WIDTH == 8
+				float t8[8] ; int32_t c8[8] ;
+				node_children8( n, idir, ood, tmin, tbest_s, t8, c8 ) ;
+				if ( t8[0] == INFINITY )
+					cur = st.pop() ;
+				else {
+#pragma unroll
+					for ( int k = 7 ; k>0 ; k-- ) if ( t8[k]<INFINITY ) st.push( c8[k] ) ;
+					cur = c8[0] ;
+				}
+				continue ;
+#endif
 				const o8 n01 = ldo( n ), n23 = ldo( n+2 ), n45 = ldo( n+4 ), n67 = ldo( n+6 ) ;
 				const q4 lx = n01.a, ly = n01.b, lz = n23.a, hx = n23.b, hy = n45.a, hz = n45.b, rf = n67.a ;
 				int32_t c0 = asint( rf.x ), c1 = asint( rf.y ), c2 = asint( rf.z ), c3 = asint( rf.w ) ;

@@ -319,13 +319,15 @@ __global__ void __launch_bounds__( 128 ) k_wide_level( const int2* frontier, uin
 			}
 		}
 	}
-	q4* o = nodes+size_t( item.y )*RTX_NODE_RECS ;
-	for ( int a = 0 ; a<3 ; a++ ) {
-		o[a]   = { lo[a][0], lo[a][1], lo[a][2], lo[a][3] } ;
-		o[3+a] = { hi[a][0], hi[a][1], hi[a][2], hi[a][3] } ;
+	for ( int h = 0 ; h<RTX_WIDTH/4 ; h++ ) {   // one 128-byte block per four children
+		q4* o = nodes+size_t( item.y )*RTX_NODE_RECS+8*h ;
+		for ( int a = 0 ; a<3 ; a++ ) {
+			o[a]   = { lo[a][4*h], lo[a][4*h+1], lo[a][4*h+2], lo[a][4*h+3] } ;
+			o[3+a] = { hi[a][4*h], hi[a][4*h+1], hi[a][4*h+2], hi[a][4*h+3] } ;
+		}
+		o[6] = { __int_as_float( ref[4*h] ), __int_as_float( ref[4*h+1] ), __int_as_float( ref[4*h+2] ), __int_as_float( ref[4*h+3] ) } ;
+		o[7] = { 0.f, 0.f, 0.f, 0.f } ;
 	}
-	o[6] = { __int_as_float( ref[0] ), __int_as_float( ref[1] ), __int_as_float( ref[2] ), __int_as_float( ref[3] ) } ;
-	o[7] = { 0.f, 0.f, 0.f, 0.f } ;
 }
 
 // ---- primitive boxes -------------------------------------------------------------------

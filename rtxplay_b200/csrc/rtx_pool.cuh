@@ -245,6 +245,20 @@ template <class P> RTX_HD int step_node( P& p, int slot, const SceneDev& S ) {
 	const float tmin = 1e-3f ;
 	const q4* n = ldp<P, q4>( p, F_NODES0, slot )+size_t( cur )*RTX_NODE_RECS ;
 	RTX_COUNT( nodes ) ;
+#if RTX_WIDTH == 8
+	{
+		float t8[8] ; int32_t c8[8] ;
+		node_children8( n, idir, ood, tmin, tbest_s, t8, c8 ) ;
+		if ( t8[0] == INFINITY )
+			cur = pop_next( p, slot, S, sp, level ) ;
+		else {
+#pragma unroll
+			for ( int k = 7 ; k>0 ; k-- ) if ( t8[k]<INFINITY ) p.push( slot, sp, c8[k], t8[k] ) ;
+			cur = c8[0] ;
+		}
+		return finish_step( p, slot, cur, sp, level ) ;
+	}
+#endif
 	const o8 n01 = ldo( n ), n23 = ldo( n+2 ), n45 = ldo( n+4 ), n67 = ldo( n+6 ) ;
 	const q4 lx = n01.a, ly = n01.b, lz = n23.a, hx = n23.b, hy = n45.a, hz = n45.b, rf = n67.a ;
 	int32_t c0 = asint( rf.x ), c1 = asint( rf.y ), c2 = asint( rf.z ), c3 = asint( rf.w ) ;

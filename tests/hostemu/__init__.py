@@ -10,6 +10,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 
+def use(name="libhostemu.so"):
+    """Select a build of the harness (libhostemu_w8.so: the experimental 8-wide hierarchy)."""
+    global _LIB
+    subprocess.check_call(["make", "-C", _HERE, name], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    _LIB = ctypes.CDLL(os.path.join(_HERE, name))
+    return _LIB
+
+
 def lib():
     global _LIB
     if _LIB is None:

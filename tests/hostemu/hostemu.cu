@@ -159,12 +159,14 @@ void build_tree( const std::vector<q4>& plo, const std::vector<q4>& phi, Tree& T
 				}
 			}
 			if ( T.nodes.size()<size_t( n_nodes )*RTX_NODE_RECS ) T.nodes.resize( size_t( n_nodes )*RTX_NODE_RECS, q4{ 0, 0, 0, 0 } ) ;
-			q4* o = T.nodes.data()+size_t( item.y )*RTX_NODE_RECS ;
-			for ( int a = 0 ; a<3 ; a++ ) {
-				o[a]   = { lo[a][0], lo[a][1], lo[a][2], lo[a][3] } ;
-				o[3+a] = { hi[a][0], hi[a][1], hi[a][2], hi[a][3] } ;
+			for ( int hh = 0 ; hh<RTX_WIDTH/4 ; hh++ ) {
+				q4* o = T.nodes.data()+size_t( item.y )*RTX_NODE_RECS+8*hh ;
+				for ( int a = 0 ; a<3 ; a++ ) {
+					o[a]   = { lo[a][4*hh], lo[a][4*hh+1], lo[a][4*hh+2], lo[a][4*hh+3] } ;
+					o[3+a] = { hi[a][4*hh], hi[a][4*hh+1], hi[a][4*hh+2], hi[a][4*hh+3] } ;
+				}
+				o[6] = { asfloat( ref[4*hh] ), asfloat( ref[4*hh+1] ), asfloat( ref[4*hh+2] ), asfloat( ref[4*hh+3] ) } ;
 			}
-			o[6] = { asfloat( ref[0] ), asfloat( ref[1] ), asfloat( ref[2] ), asfloat( ref[3] ) } ;
 		}
 		front.swap( next ) ;
 	}

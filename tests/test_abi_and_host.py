@@ -138,6 +138,32 @@ def test_reference_variants_on_host(mode, ndiv, depth, variant):
         assert int(r1["fix"].sum() >> 32) > int(r2["fix"].sum() >> 32)
 
 
+def test_eight_wide_hierarchy_on_host():
+    """-DRTX_WIDTH=8 (measured and not shipped): other trees, the same frame --
+    closest hits do not depend on the hierarchy."""
+    sp = scenes.book1(seed=3)
+    tab, meshes = scenes.table(sp, "mesh", 3)
+    cam = api.camera_table(api.camera(aspratio=1.5))
+    w, h, spp = 60, 40, 2
+    f = orc.render(orc.F32_PCG, tab, cam, w, h, spp, 50, want_first=True, meshes=meshes)
+    try:
+        hostemu.use("libhostemu_w8.so")
+        hostemu.stats()
+        for pool in (True, False):
+            e = hostemu.render(tab, cam, w, h, spp, 50, meshes=meshes, pool=pool)
+            assert np.array_equal(f["first_id"], e["first_id"])
+            assert np.array_equal(f["rpp"], e["rpp"])
+            assert np.array_equal(f["fix"], e["fix"])
+        s8 = hostemu.stats()
+    finally:
+        hostemu.use("libhostemu.so")
+    hostemu.stats()
+    for pool in (True, False):
+        hostemu.render(tab, cam, w, h, spp, 50, meshes=meshes, pool=pool)
+    s4 = hostemu.stats()
+    assert s8["rays"] == s4["rays"] and s8["nodes"] < .8 * s4["nodes"]      # fewer, wider steps
+
+
 def test_general_affine_instances_on_host():
     """Rotated / sheared / non-uniformly scaled mesh instances (the non-diagonal transform path)."""
     sp = scenes.affine_mix()
