@@ -392,7 +392,7 @@ long long emu_warpsim( const double* things, int n_things, int n_meshes, const f
 				}
 			}
 		} ;
-		for ( int l = 0 ; l<32 ; l++ ) { L[l].kind = policy != 1 ? K_REGEN : S_NONE ; L[l].pstate = 0 ; }
+		for ( int l = 0 ; l<32 ; l++ ) { L[l].kind = policy != 1 ? int( K_REGEN ) : int( S_NONE ) ; L[l].pstate = 0 ; }
 		int drain_k = 0 ;
 		while ( true ) {
 			int cnt[10] = { 0 } ; int vk[32] ;
@@ -401,8 +401,8 @@ long long emu_warpsim( const double* things, int n_things, int n_meshes, const f
 				int k = L[l].kind ;
 				if ( policy == 1 ) {
 					if ( L[l].pstate == 1 || ( L[l].pstate == 0 && ! exhausted ) ) n_fin++ ;
-					if ( k == K_SHADE ) k = L[l].pstate != 1 ? S_SWAP : S_WAIT ;                    // active ray finished
-					else if ( k == S_NONE ) k = L[l].pstate == 2 ? S_SWAP : ( L[l].pstate == 1 || ! exhausted ) ? S_WAIT : K_DONE ;
+					if ( k == K_SHADE ) k = L[l].pstate != 1 ? int( S_SWAP ) : int( S_WAIT ) ;                    // active ray finished
+					else if ( k == S_NONE ) k = L[l].pstate == 2 ? int( S_SWAP ) : ( L[l].pstate == 1 || ! exhausted ) ? int( S_WAIT ) : int( K_DONE ) ;
 				}
 				vk[l] = k ; cnt[k]++ ;
 			}
