@@ -30,7 +30,6 @@ uint32_t g_variant = 0 ;   // RTX_SEM_* of the following calls (emu_set_variant)
 struct HostStack {
 	int32_t v[256] ; int sp ;
 	RTX_HD void reset() { sp = 0 ; }
-	RTX_HD bool empty() const { return sp == 0 ; }
 	RTX_HD void push( int32_t x ) { v[sp++] = x ; RTX_COUNT( pushes ) ; RTX_COUNT_MAX( maxsp, sp ) ; }
 	RTX_HD int32_t pop() { return v[--sp] ; }
 } ;
