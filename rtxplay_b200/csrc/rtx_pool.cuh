@@ -33,6 +33,9 @@ namespace rtx {
 #if RTX_K == 1 && ! defined( RTX_REGPOOL )
 #define RTX_REGPOOL 1
 #endif
+#ifndef RTX_FFMA2
+#define RTX_FFMA2 0             // node step: the 24 multiply-adds of the four slab tests as 12 packed FFMA2 (rtx_core.cuh slab4)
+#endif
 #ifndef RTX_FAST_PUSH
 #define RTX_FAST_PUSH 0         // node step: the three pushes as predicated straight-line stores (RegPool::push3)
 #endif
@@ -293,10 +296,15 @@ template <class P> RTX_HD int step_node( P& p, int slot, const SceneDev& S ) {
 	const o8 n01 = ldo( n ), n23 = ldo( n+2 ), n45 = ldo( n+4 ), n67 = ldo( n+6 ) ;
 	const q4 lx = n01.a, ly = n01.b, lz = n23.a, hx = n23.b, hy = n45.a, hz = n45.b, rf = n67.a ;
 	int32_t c0 = asint( rf.x ), c1 = asint( rf.y ), c2 = asint( rf.z ), c3 = asint( rf.w ) ;
+#if RTX_FFMA2 && defined( __CUDA_ARCH__ )
+	float t0, t1, t2, t3 ;
+	slab4( lx, ly, lz, hx, hy, hz, idir, ood, tmin, tbest_s, t0, t1, t2, t3 ) ;
+#else
 	float t0 = slab( lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, idir, ood, tmin, tbest_s ) ;
 	float t1 = slab( lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, idir, ood, tmin, tbest_s ) ;
 	float t2 = slab( lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, idir, ood, tmin, tbest_s ) ;
 	float t3 = slab( lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, idir, ood, tmin, tbest_s ) ;
+#endif
 	// (unused child slots hold the box lo = hi = +inf, which no ray enters: no test needed)
 	// nearest child next, the others pushed far to near (a cheaper "nearest only" ordering was
 	// measured: 902 ms instead of 814 ms per frame -- the order of the pushed children matters)
