@@ -33,6 +33,9 @@ namespace rtx {
 #if RTX_K == 1 && ! defined( RTX_REGPOOL )
 #define RTX_REGPOOL 1
 #endif
+#ifndef RTX_LEAN_POP
+#define RTX_LEAN_POP 0          // pop_next: a bare pop-and-cull inner loop, the sentinels looked at outside of it
+#endif
 #ifndef RTX_FFMA2
 #define RTX_FFMA2 0             // node step: the 24 multiply-adds of the four slab tests as 12 packed FFMA2 (rtx_core.cuh slab4)
 #endif
@@ -233,6 +236,23 @@ template <class P> RTX_HD void begin_ray( P& p, int slot, const SceneDev& S, con
 // is handled on the way.
 template <class P> RTX_HD int32_t pop_next( P& p, int slot, const SceneDev& S, int32_t& sp, int32_t& level ) {
 	const float tbest_s = p.f( F_T, slot )*RTX_SLACK ;
+#if RTX_LEAN_POP
+	// the two sentinels sit on the stack with distance 0, so the distance cull alone ends the
+	// inner loop for them too; what was popped is looked at once, outside of it
+	while ( true ) {
+		float t ;
+		int32_t cur ;
+		do cur = p.pop( slot, sp, t ) ; while ( t>tbest_s ) ;
+		if ( cur != RTX_STK_RETURN )
+			return cur ;
+		const f3 o = ld3( p, F_OX, slot ), d = ld3( p, F_DX, slot ) ;
+		const f3 idir = mk3( safe_rcp( d.x ), safe_rcp( d.y ), safe_rcp( d.z ) ) ;
+		st3( p, F_IX, slot, idir ) ; st3( p, F_QX, slot, mk3( o.x*idir.x, o.y*idir.y, o.z*idir.z ) ) ;
+		level = -1 ;
+		p.si( F_LEVEL, slot, -1 ) ;
+		stp( p, F_NODES0, slot, S.tlas_nodes ) ; stp( p, F_TRIS0, slot, nullptr ) ;
+	}
+#endif
 	while ( true ) {
 		float t ;
 		const int32_t cur = p.pop( slot, sp, t ) ;
