@@ -164,6 +164,29 @@ def test_eight_wide_hierarchy_on_host():
     assert s8["rays"] == s4["rays"] and s8["nodes"] < .8 * s4["nodes"]      # fewer, wider steps
 
 
+@pytest.mark.parametrize("mode,ndiv", [("analytic", None), ("mesh", 3)])
+def test_lean_pop_loop_on_host(mode, ndiv):
+    """-DRTX_LEAN_POP=1 (a build option of the render kernel): the restructured
+    pop loop is shared step code -- same frame, same traversal work."""
+    sp = scenes.book1(seed=3)
+    tab, meshes = scenes.table(sp, mode, ndiv)
+    cam = api.camera_table(api.camera(aspratio=1.5))
+    w, h, spp = 60, 40, 2
+    f = orc.render(orc.F32_PCG, tab, cam, w, h, spp, 50, meshes=meshes)
+    hostemu.stats()
+    hostemu.render(tab, cam, w, h, spp, 50, meshes=meshes, want_first=False)
+    s0 = hostemu.stats()
+    try:
+        hostemu.use("libhostemu_lp.so")
+        hostemu.stats()
+        e = hostemu.render(tab, cam, w, h, spp, 50, meshes=meshes, want_first=False)
+        s1 = hostemu.stats()
+    finally:
+        hostemu.use("libhostemu.so")
+    assert np.array_equal(f["rpp"], e["rpp"]) and np.array_equal(f["fix"], e["fix"])
+    assert s0 == s1
+
+
 def test_general_affine_instances_on_host():
     """Rotated / sheared / non-uniformly scaled mesh instances (the non-diagonal transform path)."""
     sp = scenes.affine_mix()
