@@ -252,7 +252,7 @@ template <class P> RTX_HD int32_t pop_next( P& p, int slot, const SceneDev& S, i
 		p.si( F_LEVEL, slot, -1 ) ;
 		stp( p, F_NODES0, slot, S.tlas_nodes ) ; stp( p, F_TRIS0, slot, nullptr ) ;
 	}
-#endif
+#else
 	while ( true ) {
 		float t ;
 		const int32_t cur = p.pop( slot, sp, t ) ;
@@ -268,6 +268,7 @@ template <class P> RTX_HD int32_t pop_next( P& p, int slot, const SceneDev& S, i
 		if ( cur == RTX_STK_DONE || t<=tbest_s )
 			return cur ;
 	}
+#endif
 }
 
 // store the next work item and prefetch what it will read
