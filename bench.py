@@ -331,7 +331,7 @@ def run_b200(a):
             "roofline": {"bound": "hbm", "kernel": "k_render", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "bytes_per_segment": bytes_seg, "kernel_ms": k_ms,
-                         "note": "algorithmic node+primitive bytes of SURVEY.md 8(d); the working set is L1/L2 resident (`traffic` = DRAM bytes of one launch from the ncu capture, against %.1f TB of algorithmic bytes), so this is a cache-bandwidth figure quoted against the HBM peak; the kernel is bound by instruction issue, SIMD efficiency and L2 latency (DESIGN.md 4)" % (segs_launch * bytes_seg / 1e12),
+                         "note": "algorithmic node+primitive bytes of SURVEY.md 8(d); the working set is L1/L2 resident (`traffic` = DRAM bytes of one launch from the ncu capture, against %.1f TB of algorithmic bytes), so this is a cache-bandwidth figure quoted against the HBM peak; the kernel is bound by instruction issue and SIMD efficiency (DESIGN.md 4)" % (segs_launch * bytes_seg / 1e12),
                          "l2": {"achieved": achieved, "peak": l2_peak, "unit": "GB/s", "frac": achieved / l2_peak if l2_peak else None,
                                 "peak_source": "measured in this run: rtx_probe_read, 32 MiB buffer read 1000x by all SMs with ld.global.cg.v4"},
                          "fp32": {"flop_per_segment": flop_seg, "achieved_tflops": segs_launch * flop_seg / (k_ms * 1e-3) / 1e12,
