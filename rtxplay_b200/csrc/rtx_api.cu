@@ -111,6 +111,9 @@ struct rtx_ctx {
 	long long* d_guide_acc = nullptr ;   // allocated by the first frame that asks for guide layers
 	bool      guides_valid = false ;
 	uint32_t* d_pick = nullptr ;
+	uint32_t* d_fault = nullptr ;    // SceneDev::fault: set by a traversal whose stack overflowed
+	uint32_t* h_fault = nullptr ;    // pinned copy read back behind every tracing launch
+	uint64_t  stack_faults = 0 ;     // launches that reported one
 	unsigned long long* d_counter = nullptr ;
 	uint32_t* d_tile_counter = nullptr ;
 	int32_t*  d_ovf = nullptr ;      // overflow stacks of the resident render warps
@@ -340,7 +343,23 @@ SceneDev scene_dev( const rtx_ctx* c ) {
 	SceneDev S ;
 	S.tlas_nodes = c->tlas.nodes ; S.tlas_order = c->tlas.order ;
 	S.trav = c->d_trav ; S.shade = c->d_shade ; S.bsphere = c->d_bsphere ; S.n_things = c->n_things_dev ;
+	S.variant = 0 ; S.fault = c->d_fault ;
 	return S ;
+}
+
+// behind a tracing launch (stream already synchronised by the caller when `synced`): a traversal
+// that ran out of stack cannot have finished its ray correctly -- fail the call instead of
+// returning a plausible wrong frame
+void fault_fetch( rtx_ctx* c ) {
+	CK( cudaMemcpyAsync( c->h_fault, c->d_fault, sizeof( uint32_t ), cudaMemcpyDeviceToHost, c->stream ) ) ;
+}
+void fault_check( rtx_ctx* c, const char* what ) {
+	if ( *c->h_fault ) {
+		*c->h_fault = 0 ;
+		c->stack_faults++ ;
+		cudaMemsetAsync( c->d_fault, 0, sizeof( uint32_t ), c->stream ) ;
+		throw std::runtime_error( std::string( what )+": traversal stack overflow (hierarchy deeper than the 96-entry stack; result discarded)" ) ;
+	}
 }
 
 void free_frame( rtx_ctx* c ) {
@@ -398,6 +417,7 @@ void do_render( rtx_ctx* c, const rtx_params* p, bool resolve ) {
 	c->guides_valid = a.guides != 0 ;
 	CK( cudaEventRecord( c->ev0, c->stream ) ) ;
 	if ( a.depth>255u ) throw std::runtime_error( "rtx: depth above 255 is not supported" ) ;
+	if ( a.spp == 0 ) throw std::runtime_error( "rtx: spp must be at least 1" ) ;
 	const uint32_t n_tiles = ( ( a.w+RTX_TILE_W-1u )>>RTX_TILE_WLOG )*( ( a.h+RTX_TILE_H-1u )>>RTX_TILE_HLOG )*( a.chunks_full+a.chunks_taper ) ;   // work units
 	CK( cudaMemsetAsync( c->d_tile_counter, 0, sizeof( uint32_t )*( 2+2*256 ), c->stream ) ) ;   // unit counter + per-SM words
 	if ( ! a.accumulate ) {   // paths add into the buffers with atomics: start from zero (optx/camera_i.cu:52)
@@ -409,11 +429,13 @@ void do_render( rtx_ctx* c, const rtx_params* p, bool resolve ) {
 	c->launches += 1 ;
 	CK( cudaGetLastError() ) ;
 	CK( cudaEventRecord( c->ev1, c->stream ) ) ;
+	fault_fetch( c ) ;
 	if ( resolve )
 		do_resolve( c, p->spp ) ;
 	CK( cudaStreamSynchronize( c->stream ) ) ;
 	CK( cudaEventElapsedTime( &c->ms_render, c->ev0, c->ev1 ) ) ;
 	c->paths = uint64_t( a.w )*a.h*a.spp ;
+	fault_check( c, "rtx_render" ) ;
 }
 
 struct BufInfo { void* ptr ; size_t bytes ; } ;
@@ -486,6 +508,10 @@ int rtx_init( int device, rtx_ctx** out ) {
 			CK( cudaStreamSynchronize( c->stream ) ) ;
 		}
 		c->d_pick = dalloc<uint32_t>( c, 1 ) ;
+		c->d_fault = dalloc<uint32_t>( c, 1 ) ;
+		CK( cudaMemsetAsync( c->d_fault, 0, sizeof( uint32_t ), c->stream ) ) ;
+		CK( cudaMallocHost( reinterpret_cast<void**>( &c->h_fault ), sizeof( uint32_t ) ) ) ;
+		*c->h_fault = 0 ;
 		c->d_counter = dalloc<unsigned long long>( c, 1 ) ;
 		c->d_tile_counter = dalloc<uint32_t>( c, 2+2*256 ) ;
 		{	// CUDA loads kernels lazily on first launch; do it here so that build and frame
@@ -536,7 +562,8 @@ void rtx_shutdown( rtx_ctx* c ) {
 	dfree( c, c->d_tb_lo, c->n_things_dev ) ; dfree( c, c->d_tb_hi, c->n_things_dev ) ;
 	dfree( c, c->d_tp_lo, c->n_things_dev ) ; dfree( c, c->d_tp_hi, c->n_things_dev ) ;
 	free_frame( c ) ;
-	dfree( c, c->d_pick, 1 ) ; dfree( c, c->d_counter, 1 ) ; dfree( c, c->d_tile_counter, 2+2*256 ) ;
+	dfree( c, c->d_pick, 1 ) ; dfree( c, c->d_fault, 1 ) ; if ( c->h_fault ) cudaFreeHost( c->h_fault ) ;
+	dfree( c, c->d_counter, 1 ) ; dfree( c, c->d_tile_counter, 2+2*256 ) ;
 	dfree( c, c->d_ovf, size_t( c->render_grid )*RTX_POOL_R*RTX_POOL_OVF*2 ) ;
 	cudaEventDestroy( c->ev0 ) ; cudaEventDestroy( c->ev1 ) ;
 	for ( cudaEvent_t e : c->stage_ev ) if ( e ) cudaEventDestroy( e ) ;
@@ -552,25 +579,35 @@ int rtx_mesh_create( rtx_ctx* c, const float* xyz, uint32_t nv, const uint32_t* 
 	RTX_TRY( c )
 	CK( cudaSetDevice( c->device ) ) ;
 	if ( ! xyz || ! idx || nv == 0 || nt == 0 ) throw std::runtime_error( "rtx_mesh_create: empty mesh" ) ;
-	if ( nt>= ( 1u<<29 ) ) throw std::runtime_error( "rtx_mesh_create: more than 2^29 triangles in one mesh" ) ;
+	if ( nt>=( 1u<<28 ) ) throw std::runtime_error( "rtx_mesh_create: 2^28 or more triangles in one mesh (leaf references hold first<<3|count-1 in 31 bits)" ) ;
 	for ( size_t k = 0 ; k<3*size_t( nt ) ; k++ )
 		if ( idx[k]>=nv ) throw std::runtime_error( "rtx_mesh_create: index out of bounds" ) ;   // optx/object.cxx:62-67
 	Mesh m ;
 	m.nv = nv ; m.nt = nt ;
 	mesh_bsphere( xyz, nv, m.bsphere ) ;
-	m.vces = dalloc<float>( c, 3*size_t( nv ) ) ; m.ices = dalloc<uint32_t>( c, 3*size_t( nt ) ) ; m.tris = dalloc<q4>( c, RTX_TRI_RECS*size_t( nt ) ) ;
-	CK( cudaMemcpyAsync( m.vces, xyz, sizeof( float )*3*nv, cudaMemcpyHostToDevice, c->stream ) ) ;
-	CK( cudaMemcpyAsync( m.ices, idx, sizeof( uint32_t )*3*size_t( nt ), cudaMemcpyHostToDevice, c->stream ) ) ;
-	q4* plo = talloc<q4>( c, nt ) ; q4* phi = talloc<q4>( c, nt ) ;
-	CK( cudaEventRecord( c->ev0, c->stream ) ) ;
-	k_tri_bounds<<<( nt+255 )/256, 256, 0, c->stream>>>( m.vces, m.ices, nt, plo, phi ) ;
-	c->launches += 1 ;
-	lbvh_build( c, m.bvh, plo, phi, nt, RTX_LEAF_MAX, false ) ;
-	k_pack_tris<<<( nt+255 )/256, 256, 0, c->stream>>>( m.vces, m.ices, m.bvh.order, nt, m.tris ) ;
-	c->launches += 1 ;
-	CK( cudaGetLastError() ) ;
-	CK( cudaEventRecord( c->ev1, c->stream ) ) ;
-	CK( cudaStreamSynchronize( c->stream ) ) ;
+	q4* plo = nullptr ; q4* phi = nullptr ;
+	try {
+		m.vces = dalloc<float>( c, 3*size_t( nv ) ) ; m.ices = dalloc<uint32_t>( c, 3*size_t( nt ) ) ; m.tris = dalloc<q4>( c, RTX_TRI_RECS*size_t( nt ) ) ;
+		CK( cudaMemcpyAsync( m.vces, xyz, sizeof( float )*3*nv, cudaMemcpyHostToDevice, c->stream ) ) ;
+		CK( cudaMemcpyAsync( m.ices, idx, sizeof( uint32_t )*3*size_t( nt ), cudaMemcpyHostToDevice, c->stream ) ) ;
+		plo = talloc<q4>( c, nt ) ; phi = talloc<q4>( c, nt ) ;
+		CK( cudaEventRecord( c->ev0, c->stream ) ) ;
+		k_tri_bounds<<<( nt+255 )/256, 256, 0, c->stream>>>( m.vces, m.ices, nt, plo, phi ) ;
+		c->launches += 1 ;
+		lbvh_build( c, m.bvh, plo, phi, nt, RTX_LEAF_MAX, false ) ;
+		k_pack_tris<<<( nt+255 )/256, 256, 0, c->stream>>>( m.vces, m.ices, m.bvh.order, nt, m.tris ) ;
+		c->launches += 1 ;
+		CK( cudaGetLastError() ) ;
+		CK( cudaEventRecord( c->ev1, c->stream ) ) ;
+		CK( cudaStreamSynchronize( c->stream ) ) ;
+	} catch ( ... ) {
+		// a build that failed half way leaves nothing behind
+		cudaStreamSynchronize( c->stream ) ;
+		tfree( c, plo, nt ) ; tfree( c, phi, nt ) ;
+		lbvh_free( c, m.bvh ) ;
+		dfree( c, m.vces, 3*size_t( nv ) ) ; dfree( c, m.ices, 3*size_t( nt ) ) ; dfree( c, m.tris, RTX_TRI_RECS*size_t( nt ) ) ;
+		throw ;
+	}
 	float ms = 0.f ;
 	CK( cudaEventElapsedTime( &ms, c->ev0, c->ev1 ) ) ;
 	c->ms_blas += ms ;
@@ -594,6 +631,7 @@ int rtx_thing_add( rtx_ctx* c, uint32_t mesh_id, const rtx_optics* optics, uint3
 	RTX_TRY( c )
 	if ( mesh_id>=c->meshes.size() ) throw std::runtime_error( "rtx_thing_add: unknown mesh" ) ;
 	if ( optics->type<0 || optics->type>2 ) throw std::runtime_error( "rtx_thing_add: unknown optics type" ) ;
+	if ( c->things.size()>=( size_t( 1 )<<28 ) ) throw std::runtime_error( "rtx_thing_add: 2^28 things at most (leaf references)" ) ;
 	ThingHost th ;
 	th.mesh = mesh_id ; th.optics = *optics ;
 	const float ident[12] = { 1, 0, 0, 0,  0, 1, 0, 0,  0, 0, 1, 0 } ;   // optx/scene.cxx:183-188
@@ -708,7 +746,9 @@ int rtx_pick( rtx_ctx* c, const rtx_params* p, uint32_t x, uint32_t y, uint32_t*
 	c->launches += 1 ;
 	CK( cudaGetLastError() ) ;
 	CK( cudaMemcpyAsync( thing_id, c->d_pick, sizeof( uint32_t ), cudaMemcpyDeviceToHost, c->stream ) ) ;
+	fault_fetch( c ) ;
 	CK( cudaStreamSynchronize( c->stream ) ) ;
+	fault_check( c, "rtx_pick" ) ;
 	RTX_END( c )
 }
 
@@ -745,7 +785,9 @@ int rtx_primary_hits( rtx_ctx* c, const rtx_params* p ) {
 	k_primary_hits<<<tile_grid( a.w, a.h ), RTX_BLOCK, 0, c->stream>>>( a ) ;
 	c->launches += 1 ;
 	CK( cudaGetLastError() ) ;
+	fault_fetch( c ) ;
 	CK( cudaStreamSynchronize( c->stream ) ) ;
+	fault_check( c, "rtx_primary_hits" ) ;
 	RTX_END( c )
 }
 
@@ -763,8 +805,10 @@ int rtx_trace_rays( rtx_ctx* c, uint32_t n, const float* ori, const float* dir, 
 	CK( cudaGetLastError() ) ;
 	CK( cudaMemcpyAsync( id_out, d_id, sizeof( int64_t )*n, cudaMemcpyDeviceToHost, c->stream ) ) ;
 	if ( t_out ) CK( cudaMemcpyAsync( t_out, d_t, sizeof( float )*n, cudaMemcpyDeviceToHost, c->stream ) ) ;
+	fault_fetch( c ) ;
 	CK( cudaStreamSynchronize( c->stream ) ) ;
 	dfree( c, d_o, 3*size_t( n ) ) ; dfree( c, d_d, 3*size_t( n ) ) ; dfree( c, d_id, n ) ; dfree( c, d_t, n ) ;
+	fault_check( c, "rtx_trace_rays" ) ;
 	RTX_END( c )
 }
 

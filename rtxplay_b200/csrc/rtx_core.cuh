@@ -208,7 +208,18 @@ struct SceneDev {
 	const ThingShade* shade ;
 	uint32_t          n_things ;
 	uint32_t          variant ;      // RTX_SEM_* of the frame being rendered
+	uint32_t*         fault ;        // device word: bit 0 set by a traversal whose stack ran out of room (the launch is then reported as failed)
 } ;
+
+// a traversal stack ran out of room: the ray can no longer be finished correctly -- say so
+// (rtx_render* / rtx_primary_hits / rtx_trace_rays / rtx_pick fail with "traversal stack overflow")
+RTX_HD void stack_fault( uint32_t* fault ) {
+#if defined( __CUDA_ARCH__ )
+	if ( fault ) atomicOr( fault, 1u ) ;
+#else
+	if ( fault ) *fault |= 1u ;
+#endif
+}
 
 struct CameraDev { f3 eye, u, v, hvec, wvec, dvec ; float aperture ; } ;
 
@@ -330,22 +341,39 @@ RTX_HD bool tri_test( const f3& v0, const f3& e1, const f3& e2, const f3& ohi, c
 // host harness: 2/3 of them, half of all node steps) -- above all the ray that has just left
 // a small sphere and starts inside its box.  Conservative: the sphere is padded at build
 // time, the comparisons carry a margin; never decides a result.
+// Evaluated without the cancellation of |o-c|^2 - r^2 (whose float error grows with
+// (distance/radius)^2 and exceeded the pad beyond distance/radius ~ 30 -- round-1 advice): the
+// closest approach l = f + tc*d of the line to the centre carries an absolute error of a few
+// eps*|f| (f = o-c is exact to half an ulp, tc = -(f.d)/(d.d) to ~4 eps*|f|/|d|), which the
+// radius margin below covers five times over; the chord interval tc -+ h gets a relative slack.
+RTX_HD float approx_rcp( float x ) {
+#if defined( __CUDA_ARCH__ )
+	float r ;
+	asm( "rcp.approx.ftz.f32 %0, %1;" : "=f"( r ) : "f"( x ) ) ;   // 1 ulp; inside the margins
+	return r ;
+#else
+	return 1.f/x ;
+#endif
+}
 RTX_HD bool bsphere_miss( const q4& bs, const f3& o, const f3& d, float tmin, float tbest ) {
 	if ( bs.w<0.f )
 		return false ;
 	const float fx = o.x-bs.x, fy = o.y-bs.y, fz = o.z-bs.z ;
 	const float a = d.x*d.x+d.y*d.y+d.z*d.z ;
 	const float b = fx*d.x+fy*d.y+fz*d.z ;
-	const float c = fx*fx+fy*fy+fz*fz-bs.w*bs.w ;
-	const float disc = b*b-a*c ;
-	if ( disc<0.f )
-		return true ;                                   // the line misses the sphere
-	const float sq = sqrtf( disc ) ;
-	// roots (-b -+ sq)/a, the one without cancellation first, the other from the product c/a
-	const float q = b<0.f ? sq-b : -( sq+b ) ;          // q = -b + sign(-b) sq
-	const float r0 = q/a, r1 = q != 0.f ? c/q : r0 ;
-	const float t0 = fminf( r0, r1 ), t1 = fmaxf( r0, r1 ) ;
-	return t1*1.02f<tmin || t0>tbest*1.02f ;
+	const float ia = approx_rcp( a ) ;
+	const float tc = -b*ia ;
+	const float lx = fx+tc*d.x, ly = fy+tc*d.y, lz = fz+tc*d.z ;
+	const float l2 = lx*lx+ly*ly+lz*lz ;
+	const float m = 4e-6f*( fabsf( fx )+fabsf( fy )+fabsf( fz ) ) ;
+	const float r = bs.w+m ;
+	const float h2 = r*r-l2 ;
+	if ( h2<0.f )
+		return true ;                                   // the line passes the sphere
+	// half chord in t, widened by the absolute error m/|d| of tc: (sqrt(h2)+m)^2 <= h2+m(2r+m)
+	const float h = sqrtf( ( h2+m*( r+r+m ) )*ia )*1.00001f ;
+	const float slack = 1e-5f*fabsf( tc ) ;
+	return tc+h+slack<tmin || tc-h-slack>tbest ;        // (a NaN from a degenerate ray compares false: no cull)
 }
 
 // order-independent closest-hit rule = things.h:27-33 scanned in thing/primitive order:

@@ -22,12 +22,14 @@ namespace rtx {
 struct DevStack {
 	int32_t* base ;
 	int32_t  sp ;
+	uint32_t* fault ;   // SceneDev::fault
 	int32_t  ovf[RTX_OVF_STACK] ;
 	__device__ __forceinline__ void reset() { sp = 0 ; }
 	__device__ __forceinline__ bool empty() const { return sp == 0 ; }
 	__device__ __forceinline__ void push( int32_t v ) {
 		if ( sp<RTX_SM_STACK ) base[sp*RTX_BLOCK] = v ;
 		else if ( sp<RTX_SM_STACK+RTX_OVF_STACK ) ovf[sp-RTX_SM_STACK] = v ;
+		else stack_fault( fault ) ;
 		sp++ ;
 	}
 	__device__ __forceinline__ int32_t pop() {
@@ -158,11 +160,13 @@ __global__ void RTX_RENDER_BOUNDS k_render( const __grid_constant__ FrameArgs a,
 	__shared__ uint32_t cold_words[( RTX_COLD_WORDS>0 ? RTX_COLD_WORDS : 1 )*32] ;
 	p.cold = uint32_t( __cvta_generic_to_shared( cold_words+lane ) ) ;
 	p.ovf = ovf_all+( size_t( blockIdx.x )*RTX_POOL_R+lane )*RTX_POOL_OVF*2 ;
+	p.fault = a.S.fault ;
 #else
 	__shared__ uint32_t words[F_WORDS*RTX_POOL_R] ;
 	DevPool p ;
 	p.w = words ;
 	p.ovf = ovf_all+size_t( blockIdx.x )*RTX_POOL_R*RTX_POOL_OVF*2 ;
+	p.fault = a.S.fault ;
 #endif
 	const uint32_t tiles_x = ( a.w+RTX_TILE_W-1u )>>RTX_TILE_WLOG, tiles_y = ( a.h+RTX_TILE_H-1u )>>RTX_TILE_HLOG, n_tiles = tiles_x*tiles_y ;
 	const uint32_t n_chunks = a.chunks_full+a.chunks_taper ;
@@ -363,7 +367,7 @@ __global__ void __launch_bounds__( RTX_BLOCK ) k_primary_hits( const FrameArgs a
 	const bool valid = tile_pixel( a.w, a.h, x, y ) ;
 	const uint32_t pix = a.w*y+x ;
 	DevStack st ;
-	st.base = stack_mem+threadIdx.x ;
+	st.base = stack_mem+threadIdx.x ; st.fault = a.S.fault ;
 	Pcg rng ;
 	rng.seed( a.seed, pix, a.sample0 ) ;
 	f3 ori, dir ;
@@ -381,7 +385,7 @@ __global__ void __launch_bounds__( RTX_BLOCK ) k_primary_hits( const FrameArgs a
 __global__ void k_pick( const FrameArgs a, uint32_t px, uint32_t py, uint32_t* pick_id ) {
 	__shared__ int32_t stack_mem[RTX_SM_STACK*RTX_BLOCK] ;
 	DevStack st ;
-	st.base = stack_mem+threadIdx.x ;
+	st.base = stack_mem+threadIdx.x ; st.fault = a.S.fault ;
 	Pcg rng ;
 	rng.seed( a.seed, a.w*py+px, a.sample0 ) ;
 	f3 ori, dir ;
@@ -399,7 +403,7 @@ __global__ void __launch_bounds__( RTX_BLOCK ) k_trace_rays( const SceneDev S, u
 	const bool valid = r<n ;
 	const uint32_t q = valid ? r : 0u ;
 	DevStack st ;
-	st.base = stack_mem+threadIdx.x ;
+	st.base = stack_mem+threadIdx.x ; st.fault = S.fault ;
 	const f3 o = mk3( ori[3*size_t( q )], ori[3*size_t( q )+1], ori[3*size_t( q )+2] ) ;
 	const f3 d = mk3( dir[3*size_t( q )], dir[3*size_t( q )+1], dir[3*size_t( q )+2] ) ;
 	HitRec hit ;

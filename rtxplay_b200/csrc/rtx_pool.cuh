@@ -34,13 +34,13 @@ namespace rtx {
 #define RTX_REGPOOL 1
 #endif
 #ifndef RTX_LEAN_POP
-#define RTX_LEAN_POP 0          // pop_next: a bare pop-and-cull inner loop, the sentinels looked at outside of it
+#define RTX_LEAN_POP 1          // pop_next: a bare pop-and-cull inner loop, the sentinels looked at outside of it (r2: 681.1 -> 666.9 ms)
 #endif
 #ifndef RTX_FFMA2
-#define RTX_FFMA2 0             // node step: the 24 multiply-adds of the four slab tests as 12 packed FFMA2 (rtx_core.cuh slab4)
+#define RTX_FFMA2 1             // node step: the 24 multiply-adds of the four slab tests as 12 packed FFMA2 (rtx_core.cuh slab4; r2: 681.1 -> 674.4 ms)
 #endif
 #ifndef RTX_FAST_PUSH
-#define RTX_FAST_PUSH 0         // node step: the three pushes as predicated straight-line stores (RegPool::push3)
+#define RTX_FAST_PUSH 1         // node step: the three pushes as predicated straight-line stores (RegPool::push3; r2: 681.1 -> 666.6 ms; all three: 648.7)
 #endif
 #ifndef RTX_PREFETCH
 #define RTX_PREFETCH 0          // L1 prefetches beyond the first line of the next leaf (bits: 1 its second line, 2 / 4 the second-nearest child when a leaf / a node)
@@ -70,6 +70,7 @@ enum { K_DONE = 0, K_NODE = 1, K_LEAF = 2, K_THING = 3, K_SHADE = 4, K_REGEN = 5
 struct DevPool {
 	uint32_t* w ;      // this warp's words, [F_WORDS][R]
 	int32_t*  ovf ;    // this warp's overflow area, [R][RTX_POOL_OVF]
+	uint32_t* fault ;  // SceneDev::fault
 	__device__ __forceinline__ float    f( int fld, int slot ) const { return __uint_as_float( w[fld*( 32*RTX_K )+slot] ) ; }
 	__device__ __forceinline__ int32_t  i( int fld, int slot ) const { return int32_t( w[fld*( 32*RTX_K )+slot] ) ; }
 	__device__ __forceinline__ void     sf( int fld, int slot, float v ) { w[fld*( 32*RTX_K )+slot] = __float_as_uint( v ) ; }
@@ -81,7 +82,8 @@ struct DevPool {
 		} else if ( sp<RTX_POOL_STACK+RTX_POOL_OVF ) {
 			ovf[( slot*RTX_POOL_OVF+( sp-RTX_POOL_STACK ) )*2] = v ;
 			ovf[( slot*RTX_POOL_OVF+( sp-RTX_POOL_STACK ) )*2+1] = __float_as_int( t ) ;
-		}
+		} else
+			stack_fault( fault ) ;
 		sp++ ;
 	}
 	__device__ __forceinline__ int32_t  pop( int slot, int32_t& sp, float& t ) {
@@ -134,6 +136,7 @@ struct RegPool {
 	uint32_t  stk ;    // shared-space byte address of this lane's stack column (entry i at stk + i*256: ref, +128: distance)
 	uint32_t  cold ;   // shared-space byte address of this lane's column of cold fields (field s at cold + s*128)
 	int32_t*  ovf ;    // this lane's overflow entries (pairs)
+	uint32_t* fault ;  // SceneDev::fault
 	__device__ __forceinline__ uint32_t ldc( int s ) const { uint32_t v ; asm volatile( "ld.shared.u32 %0, [%1];" : "=r"( v ) : "r"( cold+uint32_t( s )*128u ) : "memory" ) ; return v ; }
 	__device__ __forceinline__ void     stc( int s, uint32_t v ) { asm volatile( "st.shared.u32 [%0], %1;" :: "r"( cold+uint32_t( s )*128u ), "r"( v ) : "memory" ) ; }
 	__device__ __forceinline__ float    f( int fld, int ) const { return __uint_as_float( cold_slot( fld )>=0 ? ldc( cold_slot( fld ) ) : r[fld] ) ; }
@@ -145,6 +148,7 @@ struct RegPool {
 			const uint32_t a = stk+uint32_t( sp )*256u ;
 			asm volatile( "st.shared.u32 [%0], %1;\n\tst.shared.f32 [%0+128], %2;" :: "r"( a ), "r"( v ), "f"( t ) : "memory" ) ;
 		} else if ( sp<RTX_POOL_STACK+RTX_POOL_OVF ) { ovf[2*( sp-RTX_POOL_STACK )] = v ; ovf[2*( sp-RTX_POOL_STACK )+1] = __float_as_int( t ) ; }
+		else stack_fault( fault ) ;
 		sp++ ;
 	}
 #if RTX_FAST_PUSH
@@ -188,6 +192,18 @@ struct RegPool {
 		return ovf[2*( sp-RTX_POOL_STACK )] ;
 	}
 } ;
+#endif
+
+// the hits of a node step behind the nearest one, far to near (misses carry +inf)
+template <class P> RTX_HD void push_far_children( P& p, int slot, int32_t& sp, int32_t c1, float t1, int32_t c2, float t2, int32_t c3, float t3 ) {
+	if ( t3<INFINITY ) p.push( slot, sp, c3, t3 ) ;
+	if ( t2<INFINITY ) p.push( slot, sp, c2, t2 ) ;
+	if ( t1<INFINITY ) p.push( slot, sp, c1, t1 ) ;
+}
+#if RTX_FAST_PUSH && defined( __CUDACC__ )
+__device__ __forceinline__ void push_far_children( RegPool& p, int slot, int32_t& sp, int32_t c1, float t1, int32_t c2, float t2, int32_t c3, float t3 ) {
+	p.push3( slot, sp, c1, t1, c2, t2, c3, t3 ) ;
+}
 #endif
 
 template <class P> RTX_HD f3 ld3( const P& p, int fld, int slot ) { return mk3( p.f( fld, slot ), p.f( fld+1, slot ), p.f( fld+2, slot ) ) ; }
@@ -335,13 +351,7 @@ template <class P> RTX_HD int step_node( P& p, int slot, const SceneDev& S ) {
 	if ( t0 == INFINITY )
 		cur = pop_next( p, slot, S, sp, level ) ;
 	else {
-#if RTX_FAST_PUSH && defined( __CUDA_ARCH__ ) && defined( RTX_REGPOOL )
-		p.push3( slot, sp, c1, t1, c2, t2, c3, t3 ) ;
-#else
-		if ( t3<INFINITY ) p.push( slot, sp, c3, t3 ) ;
-		if ( t2<INFINITY ) p.push( slot, sp, c2, t2 ) ;
-		if ( t1<INFINITY ) p.push( slot, sp, c1, t1 ) ;
-#endif
+		push_far_children( p, slot, sp, c1, t1, c2, t2, c3, t3 ) ;
 #if RTX_PREFETCH & 2
 		// the second-nearest child, when it is a mesh leaf, is usually next but one: fetch its triangles now
 		if ( t1<INFINITY && c1<0 && level>=0 ) prefetch_line( ldp<P, q4>( p, F_TRIS0, slot )+size_t( uint32_t( ~c1 )>>3 )*RTX_TRI_RECS ) ;

@@ -131,3 +131,47 @@ def warpsim(things, cam, w, h, unit_spp=64, units_per_warp=16, tile_step=97, dep
         if out[k]:
             r[names[k]] = (out[k] / out[16], out[8 + k] / out[k])   # iterations per ray, lanes per iteration
     return r
+
+
+def _mesh_args(meshes):
+    meshes = meshes or []
+    v = [np.ascontiguousarray(m[0], dtype=np.float32).reshape(-1, 3) for m in meshes]
+    i = [np.ascontiguousarray(m[1], dtype=np.uint32).reshape(-1, 3) for m in meshes]
+    n = len(meshes)
+    vp = (ctypes.c_void_p * max(n, 1))(*[a.ctypes.data for a in v])
+    ip = (ctypes.c_void_p * max(n, 1))(*[a.ctypes.data for a in i])
+    nv = np.array([len(a) for a in v] or [0], dtype=np.uint32)
+    nt = np.array([len(a) for a in i] or [0], dtype=np.uint32)
+    return n, vp, nv, ip, nt, (v, i)
+
+
+def trace_rays(things, ori, dirs, tmin=1e-3, meshes=None, brute=False, pool=False):
+    """Closest hits of caller-supplied rays: the while-while traversal, the render kernel's step
+    functions (pool=True; tmin must be 1e-3) or the exhaustive scan."""
+    L = lib()
+    things = np.ascontiguousarray(things, dtype=np.float64).reshape(-1, 20)
+    ori = np.ascontiguousarray(ori, dtype=np.float32).reshape(-1, 3)
+    dirs = np.ascontiguousarray(dirs, dtype=np.float32).reshape(-1, 3)
+    n, vp, nv, ip, nt, keep = _mesh_args(meshes)
+    ids = np.full(len(ori), -1, dtype=np.int64)
+    ts = np.zeros(len(ori), dtype=np.float32)
+    L.emu_trace_rays(_p(things), ctypes.c_int(len(things)), ctypes.c_int(n), vp, _p(nv), ip, _p(nt), ctypes.c_int(len(ori)), _p(ori), _p(dirs),
+                     ctypes.c_float(tmin), ctypes.c_int(1 if brute else 0), ctypes.c_int(1 if pool else 0), _p(ids), _p(ts))
+    return ids, ts
+
+
+def bsphere_miss(bs, ori, dirs, tmin, tbest):
+    """rtx_core.cuh bsphere_miss on arrays: bs [n,4], ori/dirs [n,3], tmin/tbest [n] -> bool[n]."""
+    bs, ori, dirs = (np.ascontiguousarray(a, dtype=np.float32) for a in (bs, ori, dirs))
+    tmin, tbest = (np.ascontiguousarray(a, dtype=np.float32) for a in (tmin, tbest))
+    out = np.zeros(len(bs), dtype=np.uint8)
+    lib().emu_bsphere_miss(ctypes.c_int(len(bs)), _p(bs), _p(ori), _p(dirs), _p(tmin), _p(tbest), _p(out))
+    return out.astype(bool)
+
+
+def world_bsphere(xf, bs):
+    xf = np.ascontiguousarray(xf, dtype=np.float32).reshape(12)
+    bs = np.ascontiguousarray(bs, dtype=np.float64).reshape(4)
+    out = np.zeros(4, dtype=np.float32)
+    lib().emu_world_bsphere(_p(xf), _p(bs), _p(out))
+    return out

@@ -251,7 +251,7 @@ void build_scene( EmuScene& E, const double* things, int n_things, int n_meshes,
 	}
 	if ( n_things ) build_tree( plo, phi, E.tlas, 1 ) ;
 	E.S.tlas_nodes = E.tlas.nodes.data() ; E.S.tlas_order = E.tlas.order.data() ;
-	E.S.trav = E.trav.data() ; E.S.shade = E.shade.data() ; E.S.bsphere = E.bsphere.data() ; E.S.n_things = uint32_t( n_things ) ; E.S.variant = g_variant ;
+	E.S.trav = E.trav.data() ; E.S.shade = E.shade.data() ; E.S.bsphere = E.bsphere.data() ; E.S.n_things = uint32_t( n_things ) ; E.S.variant = g_variant ; E.S.fault = nullptr ;
 }
 
 } // namespace
@@ -609,6 +609,42 @@ long long emu_warpsim_pool( const double* things, int n_things, int n_meshes, co
 	out[17] = cost ;
 	return 0 ;
 }
+
+// closest hits of caller-supplied rays through the two-level hierarchy (or by exhaustive scan)
+int emu_trace_rays( const double* things, int n_things, int n_meshes, const float* const* vces, const uint32_t* nv, const uint32_t* const* ices, const uint32_t* nt,
+		int n_rays, const float* ori, const float* dir, float tmin, int brute, int use_pool, int64_t* id, float* t_out ) {
+	EmuScene E ;
+	build_scene( E, things, n_things, n_meshes, vces, nv, ices, nt ) ;
+	HostStack st ;
+	static HostPool P ;
+	for ( int r = 0 ; r<n_rays ; r++ ) {
+		const f3 o = mk3( ori[3*r], ori[3*r+1], ori[3*r+2] ), d = mk3( dir[3*r], dir[3*r+1], dir[3*r+2] ) ;
+		HitRec hr ;
+		if ( brute ) closest_brute( E.S, o, d, tmin, hr ) ;
+		else if ( ! use_pool ) closest( E.S, o, d, tmin, st, hr ) ;
+		else {
+			// the step functions of the render kernel (they use tmin = 1e-3)
+			begin_ray( P, 0, E.S, o, d ) ;
+			int kind = kind_of( P.i( F_CUR, 0 ), -1 ) ;
+			while ( kind != K_SHADE )
+				kind = kind == K_NODE ? step_node( P, 0, E.S ) : kind == K_LEAF ? step_leaf( P, 0, E.S ) : step_thing( P, 0, E.S ) ;
+			hr.t = P.f( F_T, 0 ) ; hr.thing = P.i( F_THING, 0 ) ; hr.prim = P.i( F_PRIM, 0 ) ;
+		}
+		id[r] = hr.thing<0 ? int64_t( -1 ) : ( ( int64_t( hr.thing )<<32 )|int64_t( uint32_t( hr.prim+1 ) ) ) ;
+		t_out[r] = hr.thing<0 ? -1.f : hr.t ;
+	}
+	return 0 ;
+}
+
+// the bounding-sphere pre-test alone (rtx_core.cuh bsphere_miss), for the conservativeness test
+void emu_bsphere_miss( int n, const float* bs, const float* ori, const float* dir, const float* tmin, const float* tbest, uint8_t* out ) {
+	for ( int r = 0 ; r<n ; r++ ) {
+		const q4 b = { bs[4*r], bs[4*r+1], bs[4*r+2], bs[4*r+3] } ;
+		out[r] = bsphere_miss( b, mk3( ori[3*r], ori[3*r+1], ori[3*r+2] ), mk3( dir[3*r], dir[3*r+1], dir[3*r+2] ), tmin[r], tbest[r] ) ? 1 : 0 ;
+	}
+}
+// world_bsphere of rtx_hostmath.h (the padded sphere the pre-test is given)
+void emu_world_bsphere( const float* xf, const double* bs, float* out ) { world_bsphere( xf, bs, out ) ; }
 
 // traversal counters since the last reset: rays, nodes, leaves, tris, things, spheres, enters, pushes, max stack
 void emu_stats( unsigned long long* out, int reset ) {

@@ -221,3 +221,90 @@ def test_mesh_mode_float_mirror_tracks_double():
     assert (d["first_id"] != f["first_id"]).mean() < 2e-3
     delta = np.abs(np.clip(d["sum"] / spp, 0, 1) - orc.resolve_fix(f["fix"], spp))
     assert delta.mean() < 2e-3
+
+
+def _far_small_spheres(n=60, seed=5):
+    """Small spheres 100-1500 radii away from the origin region the rays start in."""
+    rng = np.random.default_rng(seed)
+    sp = []
+    for k in range(n):
+        r = float(rng.uniform(.01, .05))
+        dist = r * float(rng.uniform(100., 1500.))
+        u = rng.normal(size=3)
+        u /= np.linalg.norm(u)
+        sp.append(scenes._sphere(tuple(u * dist), r, int(rng.integers(0, 3)), (.5, .5, .5), fuzz=.1, index=1.5, ndiv=2))
+    return sp
+
+
+def _silhouette_rays(sp, per=40, seed=6):
+    """Rays from near the origin that graze the spheres: aimed at points 0.9 .. 1.1 radii off the centre."""
+    rng = np.random.default_rng(seed)
+    ori, d = [], []
+    for s in sp:
+        c, r = np.array(s["center"]), s["radius"]
+        for _ in range(per):
+            o = rng.uniform(-.5, .5, 3)
+            ax = c - o
+            perp = np.cross(ax, rng.normal(size=3))
+            perp /= np.linalg.norm(perp)
+            ori.append(o)
+            d.append((c + perp * r * rng.uniform(.9, 1.1) - o) * rng.uniform(.2, 2.))
+    return np.array(ori, dtype=np.float32), np.array(d, dtype=np.float32)
+
+
+def test_bounding_sphere_pretest_is_conservative():
+    """the float pre-test in front of every thing visit must never cull a ray segment that
+    touches the thing's (unpadded) bounding sphere -- checked against double arithmetic for grazing rays
+    at distance/radius ratios 100 .. 1500, and for the radius-1000 ground seen from its surface."""
+    sp = _far_small_spheres()
+    ori, d = _silhouette_rays(sp, per=200)
+    per = len(ori) // len(sp)
+    bs_exact = np.repeat(np.array([list(s["center"]) + [s["radius"]] for s in sp], dtype=np.float64), per, axis=0)
+    bs_pad = np.repeat(np.array([hostemu.world_bsphere(scenes.xf_of(s), [0, 0, 0, 1]) for s in sp], dtype=np.float32), per, axis=0)
+    rng = np.random.default_rng(1)
+    tmin = np.full(len(ori), 1e-3, dtype=np.float32)
+    tbest = np.where(rng.random(len(ori)) < .5, np.inf, rng.uniform(.5, 1.5, len(ori))).astype(np.float32)
+    # double-precision truth: the parameter interval in which the ray is inside the unpadded sphere
+    o64, d64 = ori.astype(np.float64), d.astype(np.float64)
+    f = o64 - bs_exact[:, :3]
+    a = (d64 * d64).sum(1)
+    b = (f * d64).sum(1)
+    c = (f * f).sum(1) - bs_exact[:, 3] ** 2
+    disc = b * b - a * c
+    touches = disc >= 0
+    sq = np.sqrt(np.maximum(disc, 0))
+    t0, t1 = (-b - sq) / a, (-b + sq) / a
+    touches &= (t1 >= tmin) & (t0 <= tbest)
+    miss = hostemu.bsphere_miss(bs_pad, ori, d, tmin, tbest)
+    assert touches.sum() > 1000 and (~touches).sum() > 1000
+    assert not (miss & touches).any()
+    assert (miss & ~touches).mean() > .25          # ... and it still culls
+    # the ground: rays that start on the radius-1000 sphere and leave at grazing angles
+    n = 4000
+    ang = rng.uniform(0, 2 * np.pi, n)
+    p = np.stack([rng.uniform(-15, 15, n), np.zeros(n), rng.uniform(-15, 15, n)], axis=1)
+    p[:, 1] = np.sqrt(1e6 - p[:, 0] ** 2 - p[:, 2] ** 2) - 1000.
+    dd = np.stack([np.cos(ang), rng.uniform(-.02, .02, n), np.sin(ang)], axis=1)
+    g = hostemu.world_bsphere([1000, 0, 0, 0, 0, 1000, 0, -1000, 0, 0, 1000, 0], [0, 0, 0, 1])
+    o32, d32 = p.astype(np.float32), dd.astype(np.float32)
+    f = o32.astype(np.float64) - np.array([0., -1000., 0.])
+    a, b, c = (d32.astype(np.float64) ** 2).sum(1), (f * d32).sum(1), (f * f).sum(1) - 1e6
+    disc = b * b - a * c
+    t1 = (-b + np.sqrt(np.maximum(disc, 0))) / a
+    touches = (disc >= 0) & (t1 >= 1e-3)
+    miss = hostemu.bsphere_miss(np.tile(g, (n, 1)), o32, d32, np.full(n, 1e-3, np.float32), np.full(n, np.inf, np.float32))
+    assert touches.sum() > 500 and not (miss & touches).any()
+
+
+@pytest.mark.parametrize("mode", ["analytic", "mesh"])
+def test_far_small_things_equal_oracle_on_host(mode):
+    """Small things far from the ray origins (distance/radius 100 .. 1500): the hierarchy with its
+    pre-test returns the oracle's hits for rays that graze them."""
+    sp = _far_small_spheres()
+    tab, meshes = scenes.table(sp, mode)
+    ori, d = _silhouette_rays(sp)
+    rid, rts = orc.trace_rays_f32(tab, ori, d, meshes=meshes)
+    for pool in (False, True):
+        ids, ts = hostemu.trace_rays(tab, ori, d, meshes=meshes, pool=pool)
+        assert np.array_equal(ids, rid) and np.array_equal(ts, rts)
+    assert .2 < (rid >= 0).mean() < .8
