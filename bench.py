@@ -60,6 +60,8 @@ def parse():
     ap.add_argument("--no-count", action="store_true", help="skip the counted-work leg (instrumented library)")
     ap.add_argument("--count-spp", type=int, default=4, help="samples per pixel of the counted-work frame")
     ap.add_argument("--count-worker", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--cpu-worker", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--no-rtow", action="store_true", help="skip the run of the unmodified reference binary oracle/_ref/rtow (~80 s on one core)")
     return ap.parse_args()
 
 
@@ -103,10 +105,63 @@ def cpu_leg(a, spp, steps=1, warmup=0):
     return segs / total, cores, desc, 1e3 * total / max(steps, 1)
 
 
+def cpu_worker(a):
+    """Child process of the GPU arm: the oracle is loaded here, never in the process that drives the GPU."""
+    v, cores, desc, ms = cpu_leg(a, a.cpu_spp)
+    print("CPULEG " + json.dumps({"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}), flush=True)
+
+
+def cpu_leg_child(a):
+    argv = [sys.executable, os.path.abspath(__file__), "--cpu-worker", "--width", str(a.width), "--height", str(a.height), "--depth", str(a.depth),
+            "--spp", str(a.spp), "--seed", str(a.seed), "--scene", a.scene, "--cpu-spp", str(a.cpu_spp)]
+    try:
+        out = subprocess.run(argv, capture_output=True, text=True, timeout=600)
+        return json.loads([l for l in out.stdout.splitlines() if l.startswith("CPULEG ")][-1][7:])
+    except Exception as e:
+        return {"unavailable": "cpu baseline run failed: %s" % e}
+
+
+RTOW_PATHS = 1280 * 720 * 10            # rtow.cxx:85, 96-99: hard-coded image and samples
+RTOW_SEG_PER_PATH = 1625532 / 600000.   # instrumented-reference path statistic (SURVEY.md 8c; tests/golden/rtow_pin.npz stat_300x200)
+RTOW_MD5 = "2c912270982463c81cf15fc57be2a8d6"
+
+
+class RtowRun:
+    """The UNMODIFIED reference program (oracle/_ref/rtow = g++ -O2 /root/reference/rtow.cxx, built by
+    oracle/Makefile where the reference tree exists) timed on one host core beside the GPU run
+    (/root/reference/rtow.cxx:82-122: single-threaded, no options: 1280x720, 10 spp, depth 50,
+    its own rand()-built scene).  Started before the GPU legs, collected after them."""
+
+    def __init__(self):
+        self.exe = os.path.join(ROOT, "oracle", "_ref", "rtow")
+        self.proc, self.t0 = None, None
+        if os.path.exists(self.exe):
+            self.t0 = time.perf_counter()
+            self.proc = subprocess.Popen([self.exe], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL)
+
+    def result(self):
+        if self.proc is None:
+            return {"unavailable": "oracle/_ref/rtow not built (needs /root/reference at build time)"}
+        import hashlib
+        try:
+            out, _ = self.proc.communicate(timeout=900)
+        except Exception as e:
+            self.proc.kill()
+            return {"unavailable": "rtow run failed: %s" % e}
+        wall = time.perf_counter() - self.t0
+        md5 = hashlib.md5(out).hexdigest()
+        return {"kind": "reference", "binary": "oracle/_ref/rtow (g++ -O2, unmodified /root/reference/rtow.cxx)", "cores": 1,
+                "sample": "the program as shipped: 1280x720, 10 spp, depth 50, its own 487-sphere scene (no options exist)",
+                "wall_s": wall, "paths_per_s": RTOW_PATHS / wall, "value": RTOW_PATHS * RTOW_SEG_PER_PATH / wall, "unit": UNIT,
+                "segments_per_path": RTOW_SEG_PER_PATH, "md5": md5, "md5_is_the_pinned_one": md5 == RTOW_MD5,
+                "note": "ran concurrently with the GPU legs of this bench (one of the host's cores)"}
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    rtow = None if a.no_rtow else RtowRun()
     val, cores, desc, ms = cpu_leg(a, a.cpu_spp, steps=max(a.steps, 1), warmup=min(a.warmup, 1))
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
@@ -117,6 +172,8 @@ def run_reference(a):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if rtow is not None:
+        line["cpu_baseline"]["reference_binary"] = rtow.result()
     print(json.dumps(line), flush=True)
 
 
@@ -272,6 +329,7 @@ def run_b200(a):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.tolist()
 
+    rtow = RtowRun() if (rank == 0 and world == 1 and not a.no_cpu and not a.no_rtow) else None
     for _ in range(max(a.warmup, 0)):
         flush.fill_(1)
         frame(False)
@@ -350,8 +408,10 @@ def run_b200(a):
                 cnt["frac_l2"] = cnt["achieved_gbs"] / l2_peak if l2_peak else None
             line["roofline"]["counted"] = cnt
         if not a.no_cpu and world == 1:
-            v, cores, desc, _ = cpu_leg(a, a.cpu_spp)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+            ref_bin = rtow.result() if rtow is not None else None      # (collect the one-core run first: the port then has every core)
+            line["cpu_baseline"] = cpu_leg_child(a)
+            if ref_bin is not None:
+                line["cpu_baseline"]["reference_binary"] = ref_bin
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line), flush=True)
@@ -365,6 +425,8 @@ def main():
     a = parse()
     if a.count_worker:
         count_worker(a)
+    elif a.cpu_worker:
+        cpu_worker(a)
     elif a.impl == "reference":
         run_reference(a)
     else:

@@ -828,12 +828,26 @@ void orc_resolve_fix( const uint64_t* fix, uint64_t total_spp, size_t npix, floa
 }
 
 // optx/postproc.cu:2-16, 36-47 (sRGB) and :18-34 (none)
+// x^(1/2.4) of the sRGB transfer (optx/postproc.cu:2-16 calls powf, which no two libraries round
+// alike): here, as in the CUDA path, one stated sequence of IEEE double operations -- the cube
+// root by 14 Newton steps from 1 (x in [0.0031308, 1]: converged after 10), then
+// x^(5/12) = sqrt(sqrt(c^5)) -- rounded to float once.  Every step is a correctly rounded basic
+// operation, so host and device agree bit for bit.
+static float srgb_pow( float x ) {
+	const double v = double( x ) ;
+	double c = 1. ;
+	for ( int i = 0 ; i<14 ; i++ )
+		c = ( 2.*c+v/( c*c ) )*( 1./3. ) ;
+	const double c2 = c*c ;
+	return float( std::sqrt( std::sqrt( ( c2*c2 )*c ) ) ) ;
+}
+
 void orc_srgb8( const float* raw, size_t npix, int srgb, uint8_t* rgba ) {
 	for ( size_t p = 0 ; p<npix ; p++ ) {
 		for ( int c = 0 ; c<3 ; c++ ) {
 			float v = raw[3*p+c] ;
 			if ( srgb )
-				v = v<.0031308f ? 12.92f*v : 1.055f*powf( v, 1.f/2.4f )-.055f ;
+				v = v<.0031308f ? 12.92f*v : 1.055f*srgb_pow( v )-.055f ;
 			rgba[4*p+c] = static_cast<unsigned char>( v*255 ) ;
 		}
 		rgba[4*p+3] = 255u ;

@@ -4,6 +4,7 @@
 // point that computes launches CUDA kernels, and rtx_init fails without a device.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -16,10 +17,17 @@
 #include "rtx_core.cuh"
 #include "rtx_lbvh.cuh"
 #include "rtx_kernels.cuh"
+#include "rtx_qkernel.cuh"
 #include "rtx_hostmath.h"
 
 using namespace rtx ;
 
+#ifndef RTX_DEFAULT_KERNEL
+#define RTX_DEFAULT_KERNEL 0            // 0: k_render (one ray per lane, state in registers), 1: k_render_q (compacting ray pool); RTX_KERNEL=reg|q overrides
+#endif
+#ifndef RTX_Q_DEFAULT_CARVEOUT
+#define RTX_Q_DEFAULT_CARVEOUT 60       // k_render_q: 7 CTAs x 18.5 KB of ray slots fit 60 % of the 228 KB; the rest is L1
+#endif
 #ifndef RTX_DEFAULT_CARVEOUT
 // 20 render CTAs x (4 KB stack + 1 KB the driver reserves) = 100 KB of shared memory; the rest
 // of the 228 KB is L1 for the hierarchy.  Measured: 30-35 % best, 40-44 % 1 % slower, 50 % 3-5 %
@@ -28,7 +36,7 @@ using namespace rtx ;
 #endif
 
 static_assert( sizeof( ThingTrav ) == 128, "ThingTrav layout" ) ;
-static_assert( sizeof( ThingShade ) == 144, "ThingShade layout" ) ;
+static_assert( sizeof( ThingShade ) == 160, "ThingShade layout" ) ;
 static_assert( sizeof( q4 ) == 16, "q4 layout" ) ;
 
 namespace {
@@ -118,6 +126,10 @@ struct rtx_ctx {
 	uint32_t* d_tile_counter = nullptr ;
 	int32_t*  d_ovf = nullptr ;      // overflow stacks of the resident render warps
 	uint32_t  render_grid = 0 ;
+	int       kernel = RTX_DEFAULT_KERNEL ;   // which path-tracing kernel do_render launches
+	uint32_t  q_grid = 0 ;           // k_render_q: resident warps, their cold ray records and overflow stacks
+	q4*       d_qcold = nullptr ;
+	int32_t*  d_qovf = nullptr ;
 
 	// statistics
 	uint64_t bytes = 0 ;
@@ -344,6 +356,15 @@ SceneDev scene_dev( const rtx_ctx* c ) {
 	S.tlas_nodes = c->tlas.nodes ; S.tlas_order = c->tlas.order ;
 	S.trav = c->d_trav ; S.shade = c->d_shade ; S.bsphere = c->d_bsphere ; S.n_things = c->n_things_dev ;
 	S.variant = 0 ; S.fault = c->d_fault ;
+	// arena: the lowest node / triangle array (rtx_qpool.cuh addresses them as 16-byte offsets in 32 bits)
+	uintptr_t lo = ~uintptr_t( 0 ), hi = 0 ;
+	auto span = [&]( const void* ptr, size_t bytes ) { if ( ptr ) { lo = std::min( lo, uintptr_t( ptr ) ) ; hi = std::max( hi, uintptr_t( ptr )+bytes ) ; } } ;
+	span( c->tlas.nodes, size_t( c->tlas.cap_nodes )*RTX_NODE_RECS*sizeof( q4 ) ) ;
+	for ( const Mesh& m : c->meshes ) { span( m.bvh.nodes, size_t( m.bvh.cap_nodes )*RTX_NODE_RECS*sizeof( q4 ) ) ; span( m.tris, size_t( m.nt )*RTX_TRI_RECS*sizeof( q4 ) ) ; }
+	S.arena = reinterpret_cast<const q4*>( lo == ~uintptr_t( 0 ) ? uintptr_t( 0 ) : lo-16 ) ;   // (-16: offset 0 means "none")
+	if ( getenv( "RTX_VERBOSE" ) ) fprintf( stderr, "rtx: hierarchy arena %.1f MB at %p\n", hi>lo ? double( hi-lo )/1048576. : 0., ( const void* ) lo ) ;
+	if ( hi>lo && ( hi-lo )/16>=0xfffffff0ull )
+		S.arena = nullptr ;   // (more than 64 GB apart: do_render falls back to k_render)
 	return S ;
 }
 
@@ -424,7 +445,14 @@ void do_render( rtx_ctx* c, const rtx_params* p, bool resolve ) {
 		CK( cudaMemsetAsync( c->d_accum, 0, sizeof( uint64_t )*4*size_t( a.w )*a.h, c->stream ) ) ;
 		if ( a.guides ) CK( cudaMemsetAsync( c->d_guide_acc, 0, sizeof( long long )*6*size_t( a.w )*a.h, c->stream ) ) ;
 	}
-	if ( a.guides ) k_render<true><<<min( c->render_grid, n_tiles ), 32, 0, c->stream>>>( a, c->d_tile_counter, c->d_ovf ) ;
+	if ( c->kernel == 1 && a.S.arena == nullptr && a.S.n_things && getenv( "RTX_VERBOSE" ) ) fprintf( stderr, "rtx: hierarchy arrays too far apart for k_render_q, using k_render\n" ) ;
+	if ( c->kernel == 1 && ( a.S.arena != nullptr || a.S.n_things == 0 ) ) {
+		// one warp of the pool kernel holds RTX_QR paths: fewer warps for a small frame
+		const uint32_t grid = uint32_t( std::min<uint64_t>( c->q_grid, std::max<uint64_t>( 1, ( uint64_t( a.w )*a.h*a.spp+RTX_QR-1 )/RTX_QR ) ) ) ;
+		if ( a.guides ) k_render_q<true><<<grid, 32, RTX_Q_SMEM_BYTES, c->stream>>>( a, c->d_tile_counter, c->d_qovf, c->d_qcold ) ;
+		else            k_render_q<false><<<grid, 32, RTX_Q_SMEM_BYTES, c->stream>>>( a, c->d_tile_counter, c->d_qovf, c->d_qcold ) ;
+	}
+	else if ( a.guides ) k_render<true><<<min( c->render_grid, n_tiles ), 32, 0, c->stream>>>( a, c->d_tile_counter, c->d_ovf ) ;
 	else            k_render<false><<<min( c->render_grid, n_tiles ), 32, 0, c->stream>>>( a, c->d_tile_counter, c->d_ovf ) ;
 	c->launches += 1 ;
 	CK( cudaGetLastError() ) ;
@@ -539,6 +567,24 @@ int rtx_init( int device, rtx_ctx** out ) {
 		if ( getenv( "RTX_VERBOSE" ) ) fprintf( stderr, "rtx_init: %d render warps per SM, carveout %d %%\n", per_sm, carve ) ;
 		c->render_grid = uint32_t( per_sm )*uint32_t( prop.multiProcessorCount ) ;
 		c->d_ovf = dalloc<int32_t>( c, size_t( c->render_grid )*RTX_POOL_R*RTX_POOL_OVF*2 ) ;
+		{	// the compacting-pool kernel: ray slots in dynamic shared memory
+			if ( const char* e = getenv( "RTX_KERNEL" ) ) c->kernel = ( e[0] == 'q' || e[0] == '1' ) ? 1 : 0 ;
+			int qcarve = RTX_Q_DEFAULT_CARVEOUT ;
+			if ( const char* e = getenv( "RTX_Q_CARVEOUT" ) ) qcarve = atoi( e ) ;
+			if ( qcarve>0 && qcarve<=100 ) {
+				CK( cudaFuncSetAttribute( k_render_q<false>, cudaFuncAttributePreferredSharedMemoryCarveout, qcarve ) ) ;
+				CK( cudaFuncSetAttribute( k_render_q<true>, cudaFuncAttributePreferredSharedMemoryCarveout, qcarve ) ) ;
+			}
+			int q_per_sm = 0 ;
+			CK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &q_per_sm, k_render_q<false>, 32, RTX_Q_SMEM_BYTES ) ) ;
+			if ( q_per_sm<1 ) q_per_sm = 1 ;
+			if ( const char* e = getenv( "RTX_Q_CTAS_PER_SM" ) ) { const int v = atoi( e ) ; if ( v>=1 && v<q_per_sm ) q_per_sm = v ; }   // (tuning)
+			if ( getenv( "RTX_VERBOSE" ) ) fprintf( stderr, "rtx_init: kernel %s; pool kernel: %d warps per SM x %d ray slots (%u bytes of shared memory each), carveout %d %%\n",
+				c->kernel ? "k_render_q" : "k_render", q_per_sm, int( RTX_QR ), unsigned( RTX_Q_SMEM_BYTES ), qcarve ) ;
+			c->q_grid = uint32_t( q_per_sm )*uint32_t( prop.multiProcessorCount ) ;
+			c->d_qcold = dalloc<q4>( c, size_t( c->q_grid )*RTX_QR*4 ) ;
+			c->d_qovf = dalloc<int32_t>( c, size_t( c->q_grid )*RTX_QR*RTX_QOVF*2 ) ;
+		}
 		*out = c ;
 		return 0 ;
 	} catch ( const std::exception& e ) {
@@ -554,7 +600,7 @@ void rtx_shutdown( rtx_ctx* c ) {
 	cudaSetDevice( c->device ) ;
 	cudaStreamSynchronize( c->stream ) ;
 	for ( Mesh& m : c->meshes ) {
-		dfree( c, m.vces, 3*size_t( m.nv ) ) ; dfree( c, m.ices, 3*size_t( m.nt ) ) ; dfree( c, m.tris, RTX_TRI_RECS*size_t( m.nt ) ) ;
+		dfree( c, m.vces, 3*size_t( m.nv ) ) ; dfree( c, m.ices, 3*size_t( m.nt ) ) ; tfree( c, m.tris, RTX_TRI_RECS*size_t( m.nt ) ) ;
 		lbvh_free( c, m.bvh ) ;
 	}
 	lbvh_free( c, c->tlas ) ;
@@ -565,6 +611,7 @@ void rtx_shutdown( rtx_ctx* c ) {
 	dfree( c, c->d_pick, 1 ) ; dfree( c, c->d_fault, 1 ) ; if ( c->h_fault ) cudaFreeHost( c->h_fault ) ;
 	dfree( c, c->d_counter, 1 ) ; dfree( c, c->d_tile_counter, 2+2*256 ) ;
 	dfree( c, c->d_ovf, size_t( c->render_grid )*RTX_POOL_R*RTX_POOL_OVF*2 ) ;
+	dfree( c, c->d_qcold, size_t( c->q_grid )*RTX_QR*4 ) ; dfree( c, c->d_qovf, size_t( c->q_grid )*RTX_QR*RTX_QOVF*2 ) ;
 	cudaEventDestroy( c->ev0 ) ; cudaEventDestroy( c->ev1 ) ;
 	for ( cudaEvent_t e : c->stage_ev ) if ( e ) cudaEventDestroy( e ) ;
 	cudaStreamSynchronize( c->stream ) ;   // the stream-ordered frees above
@@ -587,7 +634,7 @@ int rtx_mesh_create( rtx_ctx* c, const float* xyz, uint32_t nv, const uint32_t* 
 	mesh_bsphere( xyz, nv, m.bsphere ) ;
 	q4* plo = nullptr ; q4* phi = nullptr ;
 	try {
-		m.vces = dalloc<float>( c, 3*size_t( nv ) ) ; m.ices = dalloc<uint32_t>( c, 3*size_t( nt ) ) ; m.tris = dalloc<q4>( c, RTX_TRI_RECS*size_t( nt ) ) ;
+		m.vces = dalloc<float>( c, 3*size_t( nv ) ) ; m.ices = dalloc<uint32_t>( c, 3*size_t( nt ) ) ; m.tris = talloc<q4>( c, RTX_TRI_RECS*size_t( nt ) ) ;   // (triangles beside the node arrays: k_render_q addresses both as offsets from one base)
 		CK( cudaMemcpyAsync( m.vces, xyz, sizeof( float )*3*nv, cudaMemcpyHostToDevice, c->stream ) ) ;
 		CK( cudaMemcpyAsync( m.ices, idx, sizeof( uint32_t )*3*size_t( nt ), cudaMemcpyHostToDevice, c->stream ) ) ;
 		plo = talloc<q4>( c, nt ) ; phi = talloc<q4>( c, nt ) ;
@@ -605,7 +652,7 @@ int rtx_mesh_create( rtx_ctx* c, const float* xyz, uint32_t nv, const uint32_t* 
 		cudaStreamSynchronize( c->stream ) ;
 		tfree( c, plo, nt ) ; tfree( c, phi, nt ) ;
 		lbvh_free( c, m.bvh ) ;
-		dfree( c, m.vces, 3*size_t( nv ) ) ; dfree( c, m.ices, 3*size_t( nt ) ) ; dfree( c, m.tris, RTX_TRI_RECS*size_t( nt ) ) ;
+		dfree( c, m.vces, 3*size_t( nv ) ) ; dfree( c, m.ices, 3*size_t( nt ) ) ; tfree( c, m.tris, RTX_TRI_RECS*size_t( nt ) ) ;
 		throw ;
 	}
 	float ms = 0.f ;

@@ -178,7 +178,7 @@ struct ThingTrav {
 	int32_t    pad ;
 } ;
 
-// per-thing record read by shading (144 bytes)
+// per-thing record read by shading (160 bytes = 5 x 32: the pool kernel fetches it with 256-bit loads)
 struct ThingShade {
 	double          xf[12] ;  // object->world
 	float           albedo[3], fuzz ;
@@ -188,6 +188,7 @@ struct ThingShade {
 	int32_t         diag ;    // as in ThingTrav
 	const float*    vces ;    // mesh vertices (xyz) and indices as uploaded
 	const uint32_t* ices ;
+	double          pad_[2] ;
 } ;
 
 // Which of the reference's own programs the path semantics follow (SURVEY.md 8a "divergences"):
@@ -208,6 +209,7 @@ struct SceneDev {
 	const ThingShade* shade ;
 	uint32_t          n_things ;
 	uint32_t          variant ;      // RTX_SEM_* of the frame being rendered
+	const q4*         arena ;        // lowest address of all node / triangle arrays: the pool kernel keeps them as 32-bit offsets (16-byte units) from here
 	uint32_t*         fault ;        // device word: bit 0 set by a traversal whose stack ran out of room (the launch is then reported as failed)
 } ;
 

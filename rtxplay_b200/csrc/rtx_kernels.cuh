@@ -443,6 +443,19 @@ __global__ void __launch_bounds__( 256 ) k_resolve_guides( const long long* gacc
 	}
 }
 
+// x^(1/2.4) of the sRGB transfer as one stated sequence of IEEE double operations (the reference's
+// powf, optx/postproc.cu:9, is rounded differently by every math library): cube root by 14 Newton
+// steps from 1 (converged after 10 for x in [0.0031308, 1]), then x^(5/12) = sqrt(sqrt(c^5)),
+// rounded to float once.  The oracle (orc_srgb8) evaluates the same sequence: 8-bit codes are bit-exact.
+__device__ __forceinline__ float srgb_pow( float x ) {
+	const double v = double( x ) ;
+	double c = 1. ;
+	for ( int i = 0 ; i<14 ; i++ )
+		c = ( 2.*c+v/( c*c ) )*( 1./3. ) ;
+	const double c2 = c*c ;
+	return float( sqrt( sqrt( ( c2*c2 )*c ) ) ) ;
+}
+
 // optx/postproc.cu:18-34 (none) and :2-16, 36-47 (sRGB): float3 -> uchar4, truncating
 __global__ void __launch_bounds__( 256 ) k_postproc( const float* raw, uchar4* dst, uint32_t npix, int srgb ) {
 	const uint32_t p = blockIdx.x*blockDim.x+threadIdx.x ;
@@ -451,7 +464,7 @@ __global__ void __launch_bounds__( 256 ) k_postproc( const float* raw, uchar4* d
 	float c[3] = { raw[3*size_t( p )], raw[3*size_t( p )+1], raw[3*size_t( p )+2] } ;
 	if ( srgb )
 		for ( int k = 0 ; k<3 ; k++ )
-			c[k] = c[k]<.0031308f ? 12.92f*c[k] : 1.055f*powf( c[k], 1.f/2.4f )-.055f ;
+			c[k] = c[k]<.0031308f ? 12.92f*c[k] : 1.055f*srgb_pow( c[k] )-.055f ;
 	dst[p] = make_uchar4( static_cast<unsigned char>( c[0]*255 ), static_cast<unsigned char>( c[1]*255 ), static_cast<unsigned char>( c[2]*255 ), 255u ) ;
 }
 

@@ -258,7 +258,11 @@ template <class P> RTX_HD int32_t pop_next( P& p, int slot, const SceneDev& S, i
 	while ( true ) {
 		float t ;
 		int32_t cur ;
+#if defined( RTX_NO_POPCULL )
+		cur = p.pop( slot, sp, t ) ;   // (experiment: no distance cull of popped entries)
+#else
 		do cur = p.pop( slot, sp, t ) ; while ( t>tbest_s ) ;
+#endif
 		if ( cur != RTX_STK_RETURN )
 			return cur ;
 		const f3 o = ld3( p, F_OX, slot ), d = ld3( p, F_DX, slot ) ;

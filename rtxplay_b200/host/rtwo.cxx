@@ -4,7 +4,10 @@
 // stderr.  Exits 1 with "exception: ..." on any failure, like the reference.
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
+#include <fstream>
 #include <iostream>
+#include <memory>
 #include <vector>
 
 #include "args.h"
@@ -76,11 +79,13 @@ class RTWO : public Scene {
 			if ( analytic_ )
 				gas_3 = gas_6 = gas_8 = gas_9 = addAnalyticSphere() ;
 			else {
-				// the reference reads sphere_{3,6,8,9}.scn written by its `sphere` tool; the
-				// same meshes are produced in memory here (Object also reads .scn files)
-				Sphere s3( 1.f, 3 ), s6( 1.f, 6 ), s8( 1.f, 8 ), s9( 1.f, 9 ) ;
-				Object sphere_3( s3.mesh() ), sphere_6( s6.mesh() ), sphere_8( s8.mesh() ), sphere_9( s9.mesh() ) ;
-				gas_3 = add( sphere_3 ) ; gas_6 = add( sphere_6 ) ; gas_8 = add( sphere_8 ) ; gas_9 = add( sphere_9 ) ;
+				// optx/rtwo.cxx:138-145: the meshes come from the scene files sphere_{3,6,8,9}.scn that the
+				// `sphere` tool writes (optx/Makefile:204-212; here: make -C rtxplay_b200/host scenes), looked
+				// up in the working directory like the reference does (or in $RTWO_SCENE_DIR).  A file that is
+				// not there is replaced by what the tool would have written: the tessellation with every
+				// coordinate passed through the file format's six decimals -- the same frame either way.
+				std::unique_ptr<Object> sphere_3 = sphere( 3 ), sphere_6 = sphere( 6 ), sphere_8 = sphere( 8 ), sphere_9 = sphere( 9 ) ;
+				gas_3 = add( *sphere_3 ) ; gas_6 = add( *sphere_6 ) ; gas_8 = add( *sphere_8 ) ; gas_9 = add( *sphere_9 ) ;
 			}
 
 			Thing thing = {} ;
@@ -138,6 +143,23 @@ class RTWO : public Scene {
 
 	private:
 		bool analytic_ ;
+
+		static std::unique_ptr<Object> sphere( const unsigned int ndiv ) {
+			const char* dir = getenv( "RTWO_SCENE_DIR" ) ;
+			const std::string file = ( dir ? std::string( dir )+"/" : std::string() )+"sphere_"+std::to_string( ndiv )+".scn" ;
+			if ( std::ifstream( file ).good() )
+				return std::unique_ptr<Object>( new Object( file ) ) ;                  // optx/object.cxx:34-93
+			Sphere s( 1.f, ndiv ) ;
+			float3* vces ; unsigned int nv ; uint3* ices ; unsigned int nt ;
+			std::tie( vces, nv, ices, nt ) = s.mesh() ;
+			std::vector<float3> rounded( vces, vces+nv ) ;
+			for ( float3& p : rounded ) {
+				char text[3][64] ;                                                      // optx/sphere.cxx:129: "v %f %f %f"
+				snprintf( text[0], sizeof( text[0] ), "%f", p.x ) ; snprintf( text[1], sizeof( text[1] ), "%f", p.y ) ; snprintf( text[2], sizeof( text[2] ), "%f", p.z ) ;
+				p.x = strtof( text[0], nullptr ) ; p.y = strtof( text[1], nullptr ) ; p.z = strtof( text[2], nullptr ) ;
+			}
+			return std::unique_ptr<Object>( new Object( Mesh( rounded.data(), nv, ices, nt ) ) ) ;
+		}
 } ;
 
 int main( int argc, char* argv[] ) {
@@ -183,12 +205,14 @@ int main( int argc, char* argv[] ) {
 		cg::launcher = &launcher ;
 		{
 			// path semantics where the reference's variants differ (include/rtx.h RTX_VARIANT_*): the
-			// reference picks its recursive programs at build time (-DRECURSIVE, optx/rtwo.cxx:44-50);
-			// here that macro, or RTWO_VARIANT=rtow|iterative|recursive at run time; default rtow.cxx
+			// reference picks its recursive programs at build time (-DRECURSIVE, optx/rtwo.cxx:44-50), its
+			// default build runs the iterative ones (optx/Makefile:57-59) -- so does this drop-in;
+			// RTWO_VARIANT=rtow|iterative|recursive chooses at run time (rtow = the CPU path's semantics,
+			// the parity target of the oracle tests)
 #ifdef RECURSIVE
 			unsigned int variant = RTX_VARIANT_RTWO_R ;
 #else
-			unsigned int variant = RTX_VARIANT_RTOW ;
+			unsigned int variant = RTX_VARIANT_RTWO_I ;
 #endif // RECURSIVE
 			if ( const char* e = getenv( "RTWO_VARIANT" ) ) {
 				const std::string v( e ) ;
@@ -220,6 +244,11 @@ int main( int argc, char* argv[] ) {
 
 		// post processing
 		const unsigned int w = lp_general.image_w, h = lp_general.image_h ;
+		if ( const char* dump = getenv( "RTWO_DUMP_RAW" ) ) {   // (test hook: rawRGB as float32 triples, rows bottom-up in memory order)
+			std::vector<float3> raw( size_t( w )*h ) ;
+			CUDA_CHECK( cudaMemcpy( raw.data(), lp_general.rawRGB, sizeof( float3 )*w*h, cudaMemcpyDeviceToHost ) ) ;
+			std::ofstream( dump, std::ios::binary ).write( reinterpret_cast<const char*>( raw.data() ), std::streamsize( sizeof( float3 )*w*h ) ) ;
+		}
 		CUDA_CHECK( cudaMalloc( reinterpret_cast<void**>( &lp_general.image ), sizeof( uchar4 )*w*h ) ) ;
 		pp_sRGB( lp_general.rawRGB, lp_general.image, w, h ) ;
 

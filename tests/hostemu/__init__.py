@@ -61,7 +61,7 @@ def render(things, cam, w, h, spp, depth=50, seed=4711, sample0=0, sample_stride
     L.emu_render(_p(things), ctypes.c_int(len(things)), ctypes.c_int(n), vp, _p(nv), ip, _p(nt), _p(cam),
                  ctypes.c_int(w), ctypes.c_int(h), ctypes.c_int(spp), ctypes.c_int(depth), ctypes.c_uint64(seed),
                  ctypes.c_int(sample0), ctypes.c_int(sample_stride), _p(fix), _p(rpp), _p(fid if want_first else None), _p(ft if want_first else None),
-                 ctypes.c_int(1 if brute else 0), ctypes.c_int(1 if pool else 0))
+                 ctypes.c_int(1 if brute else 0), ctypes.c_int(2 if pool == "q" else 1 if pool else 0))
     L.emu_set_variant(ctypes.c_int(0))
     return dict(fix=fix, rpp=rpp, first_id=fid, first_t=ft)
 
@@ -126,7 +126,8 @@ def warpsim(things, cam, w, h, unit_spp=64, units_per_warp=16, tile_step=97, dep
                   ctypes.c_int(depth), ctypes.c_uint64(seed), ctypes.c_int(policy), ctypes.c_int(sticky), ctypes.c_int(t1), ctypes.c_int(t2),
                   _p(c), _p(out))
     names = ["", "node", "leaf", "thing", "shade", "regen", "swap", "batch"]
-    r = {"rays": out[16], "paths": out[18], "cost": out[17], "cost_per_ray": out[17] / max(out[16], 1)}
+    r = {"rays": out[16], "paths": out[18], "cost": out[17], "cost_per_ray": out[17] / max(out[16], 1),
+         "node_lines_per_ray": out[19] / max(out[16], 1)}
     for k in range(1, 8):
         if out[k]:
             r[names[k]] = (out[k] / out[16], out[8 + k] / out[k])   # iterations per ray, lanes per iteration

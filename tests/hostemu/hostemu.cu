@@ -13,6 +13,7 @@
 #include "../../rtxplay_b200/csrc/rtx_core.cuh"
 #include "../../rtxplay_b200/csrc/rtx_lbvh.cuh"
 #include "../../rtxplay_b200/csrc/rtx_pool.cuh"
+#include "../../rtxplay_b200/csrc/rtx_qpool.cuh"
 #include "../../rtxplay_b200/csrc/rtx_hostmath.h"
 
 using namespace rtx ;
@@ -35,6 +36,7 @@ struct HostStack {
 } ;
 
 // one ray slot, array backed: the store the step functions of rtx_pool.cuh run on here
+unsigned long long g_sp_hist[128] ;   // stack size seen by pushes (development statistic)
 struct HostPool {
 	uint32_t w[F_WORDS] ; int32_t ovf[512] ;
 	RTX_HD float   f( int fld, int ) const { float v ; memcpy( &v, &w[fld], 4 ) ; return v ; }
@@ -43,6 +45,9 @@ struct HostPool {
 	RTX_HD void    si( int fld, int, int32_t v ) { w[fld] = uint32_t( v ) ; }
 	RTX_HD void    push( int, int32_t& sp, int32_t v, float t ) {
 		uint32_t tb ; memcpy( &tb, &t, 4 ) ;
+#if ! defined( __CUDA_ARCH__ )
+		g_sp_hist[sp<127 ? sp : 127]++ ;
+#endif
 		if ( sp<RTX_POOL_STACK ) { w[F_STACK+2*sp] = uint32_t( v ) ; w[F_STACK+2*sp+1] = tb ; }
 		else { ovf[2*( sp-RTX_POOL_STACK )] = v ; ovf[2*( sp-RTX_POOL_STACK )+1] = int32_t( tb ) ; }
 		sp++ ;
@@ -68,6 +73,67 @@ f3 pool_path( const SceneDev& S, const CameraDev& cam, uint32_t x, uint32_t y, u
 			case K_LEAF:  kind = step_leaf( P, 0, S ) ; break ;
 			case K_THING: kind = step_thing( P, 0, S ) ; break ;
 			case K_SHADE: { segments++ ; bool g ; f3 gn, ga ; uint32_t sg ; kind = step_shade( P, 0, S, c, g, gn, ga, sg ) ; break ; }
+			default: return c ;
+		}
+	}
+}
+
+
+// one slot of the compacting pool (rtx_qpool.cuh), array backed; node / triangle arrays are
+// "encoded" as indices into a small pointer table (the device uses 16-byte offsets from an arena)
+struct QHost {
+	q4 rec[RTX_QS] ; q4 cold[4] ; int32_t ovf[2*512] ;
+	std::vector<const q4*> ptrs ;
+	RTX_HD q4   ldq( int, int q ) const { return rec[q] ; }
+	RTX_HD void stq( int, int q, const q4& v ) { rec[q] = v ; }
+	RTX_HD void stw( int, int q, int w, float v ) { ( &rec[q].x )[w] = v ; }
+	RTX_HD q4   ldc( int, int q ) const { return cold[q] ; }
+	RTX_HD void stc( int, int q, const q4& v ) { cold[q] = v ; }
+	RTX_HD void stcw( int, int q, int w, float v ) { ( &cold[q].x )[w] = v ; }
+	RTX_HD void push( int, int32_t& sp, int32_t v, float t ) {
+#if ! defined( __CUDA_ARCH__ )
+		g_sp_hist[sp<127 ? sp : 127]++ ;
+#endif
+		if ( sp<RTX_QSTACK ) { float* e = &rec[6].x+2*sp ; e[0] = asfloat( v ) ; e[1] = t ; }
+		else { ovf[2*( sp-RTX_QSTACK )] = v ; ovf[2*( sp-RTX_QSTACK )+1] = asint( t ) ; }
+		sp++ ;
+	}
+	RTX_HD int32_t pop( int, int32_t& sp, float& t ) {
+		sp-- ;
+		if ( sp<RTX_QSTACK ) { const float* e = &rec[6].x+2*sp ; t = e[1] ; return asint( e[0] ) ; }
+		t = asfloat( ovf[2*( sp-RTX_QSTACK )+1] ) ;
+		return ovf[2*( sp-RTX_QSTACK )] ;
+	}
+	RTX_HD float enc( int, const q4* p ) {
+#if ! defined( __CUDA_ARCH__ )
+		if ( ! p ) return asfloat( 0 ) ;
+		for ( size_t k = 0 ; k<ptrs.size() ; k++ ) if ( ptrs[k] == p ) return asfloat( int32_t( k+1 ) ) ;
+		ptrs.push_back( p ) ;
+		return asfloat( int32_t( ptrs.size() ) ) ;
+#else
+		return 0.f ;
+#endif
+	}
+	RTX_HD const q4* dec( int, float w ) const {
+#if ! defined( __CUDA_ARCH__ )
+		return ptrs[size_t( asint( w )-1 )] ;
+#else
+		return nullptr ;
+#endif
+	}
+} ;
+
+// a whole path through the step functions of the compacting pool
+f3 qpool_path( const SceneDev& S, const CameraDev& cam, uint32_t x, uint32_t y, uint32_t w, uint32_t h, uint64_t seed, uint32_t sample, uint32_t depth, uint32_t& segments ) {
+	static QHost P ;
+	int kind = qstep_regen( P, 0, S, cam, x, y, w, h, 0u, seed, sample, depth ) ;
+	f3 c = mk3( 0.f, 0.f, 0.f ) ;
+	while ( true ) {
+		switch ( kind ) {
+			case K_NODE:  kind = qstep_node( P, 0, S ) ; break ;
+			case K_LEAF:  kind = qstep_leaf( P, 0, S ) ; break ;
+			case K_THING: kind = qstep_thing( P, 0, S ) ; break ;
+			case K_SHADE: { segments++ ; bool g ; f3 gn, ga ; uint32_t sg, pix ; kind = qstep_shade( P, 0, S, c, pix, g, gn, ga, sg ) ; break ; }
 			default: return c ;
 		}
 	}
@@ -251,7 +317,7 @@ void build_scene( EmuScene& E, const double* things, int n_things, int n_meshes,
 	}
 	if ( n_things ) build_tree( plo, phi, E.tlas, 1 ) ;
 	E.S.tlas_nodes = E.tlas.nodes.data() ; E.S.tlas_order = E.tlas.order.data() ;
-	E.S.trav = E.trav.data() ; E.S.shade = E.shade.data() ; E.S.bsphere = E.bsphere.data() ; E.S.n_things = uint32_t( n_things ) ; E.S.variant = g_variant ; E.S.fault = nullptr ;
+	E.S.trav = E.trav.data() ; E.S.shade = E.shade.data() ; E.S.bsphere = E.bsphere.data() ; E.S.n_things = uint32_t( n_things ) ; E.S.variant = g_variant ; E.S.fault = nullptr ; E.S.arena = nullptr ;
 }
 
 } // namespace
@@ -288,7 +354,8 @@ int emu_render( const double* things, int n_things, int n_meshes, const float* c
 					first_id[pix] = hr.thing<0 ? int64_t( -1 ) : ( ( int64_t( hr.thing )<<32 )|int64_t( uint32_t( hr.prim+1 ) ) ) ;
 					if ( first_t ) first_t[pix] = hr.thing<0 ? -1.f : hr.t ;
 				}
-				const f3 col = use_pool ? pool_path( E.S, c, uint32_t( x ), uint32_t( y ), uint32_t( w ), uint32_t( h ), seed, uint32_t( sample0+k*sample_stride ), uint32_t( depth ), segments )
+				const f3 col = use_pool == 2 ? qpool_path( E.S, c, uint32_t( x ), uint32_t( y ), uint32_t( w ), uint32_t( h ), seed, uint32_t( sample0+k*sample_stride ), uint32_t( depth ), segments )
+				                : use_pool ? pool_path( E.S, c, uint32_t( x ), uint32_t( y ), uint32_t( w ), uint32_t( h ), seed, uint32_t( sample0+k*sample_stride ), uint32_t( depth ), segments )
 				                        : path_radiance( E.S, ori, dir, uint32_t( depth ), rng, st, segments ) ;
 				acc[0] += tofix( col.x ) ; acc[1] += tofix( col.y ) ; acc[2] += tofix( col.z ) ;
 			}
@@ -425,6 +492,7 @@ long long emu_warpsim( const double* things, int n_things, int n_meshes, const f
 				case K_NODE:
 					while ( true ) {
 						int n = 0 ;
+						{ std::vector<const void*> seen ; for ( int l = 0 ; l<32 ; l++ ) if ( L[l].kind == K_NODE ) { const void* a = ldp<HostPool, q4>( L[l].act, F_NODES0, 0 )+size_t( L[l].act.i( F_CUR, 0 ) )*RTX_NODE_RECS ; if ( std::find( seen.begin(), seen.end(), a ) == seen.end() ) seen.push_back( a ) ; } out[19] += double( seen.size() ) ; }
 						for ( int l = 0 ; l<32 ; l++ ) if ( L[l].kind == K_NODE ) { L[l].kind = step_node( L[l].act, 0, E.S ) ; n++ ; }
 						out[K_NODE] += 1. ; out[8+K_NODE] += n ; cost += K.node ;
 						int m = 0 ;
@@ -512,6 +580,8 @@ long long emu_warpsim( const double* things, int n_things, int n_meshes, const f
 // policy 2 of the simulator: R rays per warp whose state any lane can pick up (state in shared
 // memory, compacted by kind before every step): each iteration takes up to 32 rays of the kind
 // most rays are in.  out[] as emu_warpsim.
+int g_sim_columns = 0 ;   // >0: slot r belongs to column r % columns, a step serves at most 32/columns rays per column
+void emu_sim_columns( int c ) { g_sim_columns = c ; }
 long long emu_warpsim_pool( const double* things, int n_things, int n_meshes, const float* const* vces, const uint32_t* nv, const uint32_t* const* ices, const uint32_t* nt,
 		const double* cam, int w, int h, int unit_spp, int units_per_warp, int tile_step, int depth, uint64_t seed,
 		int R, int sticky, const double* costs, double* out ) {
@@ -550,9 +620,22 @@ long long emu_warpsim_pool( const double* things, int n_things, int n_meshes, co
 		} ;
 		for ( int r = 0 ; r<R ; r++ ) kd[r] = K_REGEN ;
 		int sel[32] ;
-		auto pick = [&]( int kind ) { int n = 0 ; for ( int r = 0 ; r<R && n<32 ; r++ ) if ( kd[r] == kind ) sel[n++] = r ; return n ; } ;
+		auto pick = [&]( int kind ) {
+			int n = 0 ;
+			if ( g_sim_columns>0 ) {
+				int per[64] = { 0 } ; const int cap = 32/g_sim_columns ;
+				for ( int r = 0 ; r<R && n<32 ; r++ ) if ( kd[r] == kind && per[r%g_sim_columns]<cap ) { per[r%g_sim_columns]++ ; sel[n++] = r ; }
+				return n ;
+			}
+			for ( int r = 0 ; r<R && n<32 ; r++ ) if ( kd[r] == kind ) sel[n++] = r ;
+			return n ;
+		} ;
 		while ( true ) {
 			int cnt[8] = { 0 } ;
+			if ( g_sim_columns>0 ) {
+				int per[8][64] = { { 0 } } ; const int cap = 32/g_sim_columns ;
+				for ( int r = 0 ; r<R ; r++ ) if ( per[kd[r]][r%g_sim_columns]<cap ) { per[kd[r]][r%g_sim_columns]++ ; cnt[kd[r]]++ ; }
+			} else
 			for ( int r = 0 ; r<R ; r++ ) cnt[kd[r]]++ ;
 			int kind = K_DONE, best = 0 ;
 			for ( int k = 1 ; k<=K_REGEN ; k++ ) { const int cc = cnt[k]>32 ? 32 : cnt[k] ; if ( cc && ( ( cc<<3 )|k )>best ) { best = ( cc<<3 )|k ; kind = k ; } }
@@ -562,6 +645,7 @@ long long emu_warpsim_pool( const double* things, int n_things, int n_meshes, co
 				case K_NODE:
 					while ( true ) {
 						const int n = pick( K_NODE ) ;
+						{ std::vector<const void*> seen ; for ( int q = 0 ; q<n ; q++ ) { const void* a = ldp<HostPool, q4>( P[sel[q]], F_NODES0, 0 )+size_t( P[sel[q]].i( F_CUR, 0 ) )*RTX_NODE_RECS ; if ( std::find( seen.begin(), seen.end(), a ) == seen.end() ) seen.push_back( a ) ; } out[19] += double( seen.size() ) ; }
 						for ( int q = 0 ; q<n ; q++ ) kd[sel[q]] = step_node( P[sel[q]], 0, E.S ) ;
 						out[K_NODE] += 1. ; out[8+K_NODE] += n ; cost += K.node ;
 						int m = 0 ;
@@ -645,6 +729,8 @@ void emu_bsphere_miss( int n, const float* bs, const float* ori, const float* di
 }
 // world_bsphere of rtx_hostmath.h (the padded sphere the pre-test is given)
 void emu_world_bsphere( const float* xf, const double* bs, float* out ) { world_bsphere( xf, bs, out ) ; }
+
+void emu_sp_hist( unsigned long long* out, int reset ) { for ( int k = 0 ; k<128 ; k++ ) { out[k] = g_sp_hist[k] ; if ( reset ) g_sp_hist[k] = 0 ; } }
 
 // traversal counters since the last reset: rays, nodes, leaves, tris, things, spheres, enters, pushes, max stack
 void emu_stats( unsigned long long* out, int reset ) {
