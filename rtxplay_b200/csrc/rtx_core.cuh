@@ -14,6 +14,7 @@
 #pragma once
 
 #include <stdint.h>
+#include <string.h>
 #include <math.h>
 #include <float.h>
 
@@ -757,6 +758,131 @@ RTX_HD_CALL bool scatter( const ThingShade* ts, const f3& dir, const Frame& fr, 
 	attened = mk3( 1.f, 1.f, 1.f ) ;
 	return true ;
 }
+
+RTX_HD q4 mkq( float x, float y, float z, float w ) { q4 r ; r.x = x ; r.y = y ; r.z = z ; r.w = w ; return r ; }
+RTX_HD float ibits( int32_t i ) { return asfloat( i ) ; }
+RTX_HD float ubits( uint32_t u ) { return asfloat( int32_t( u ) ) ; }
+RTX_HD uint32_t bitsu( float f ) { return uint32_t( asint( f ) ) ; }
+RTX_HD double dbl( float lo, float hi ) {
+#if defined( __CUDA_ARCH__ )
+	return __hiloint2double( __float_as_int( hi ), __float_as_int( lo ) ) ;
+#else
+	const uint64_t b = uint64_t( bitsu( lo ) )|( uint64_t( bitsu( hi ) )<<32 ) ;
+	double d ; memcpy( &d, &b, 8 ) ; return d ;
+#endif
+}
+
+// 32 bytes of a thing record with one 256-bit load (the records are 16-byte aligned arrays of
+// 128 / 144 bytes whose 32-byte pieces never straddle the alignment a 256-bit load needs: the
+// arrays come from cudaMalloc, 256-byte aligned, and both record sizes are multiples of 16 --
+// so pieces at offsets that are multiples of 32 within a 32-byte aligned record are fine for
+// ThingTrav (128 bytes); ThingShade (144 bytes) is read with 128-bit loads)
+RTX_HD o8 ldo_rec( const void* p ) {
+#if defined( __CUDA_ARCH__ )
+	o8 r ;
+	asm( "ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		: "=f"( r.a.x ), "=f"( r.a.y ), "=f"( r.a.z ), "=f"( r.a.w ), "=f"( r.b.x ), "=f"( r.b.y ), "=f"( r.b.z ), "=f"( r.b.w ) : "l"( p ) ) ;
+	return r ;
+#else
+	o8 r ; memcpy( &r, p, 32 ) ; return r ;
+#endif
+}
+RTX_HD q4 ldq_rec( const void* p ) {
+#if defined( __CUDA_ARCH__ )
+	const float4 v = __ldg( reinterpret_cast<const float4*>( p ) ) ;
+	return mkq( v.x, v.y, v.z, v.w ) ;
+#else
+	q4 r ; memcpy( &r, p, 16 ) ; return r ;
+#endif
+}
+
+// ---- shading without calls and without local memory (the __noinline__ frame_of / scatter of
+// rtx_core.cuh pass their structures through the stack): the same expressions in the same order
+// -- sphere.h:40-45 / optx/optics_i.cu:40-82, :259-267 and optics.h:15-24, :34-40, :51-68 -- on
+// thing records fetched with 256-bit loads.  `mat` returns albedo.rgb, fuzz | index, type, kind, diag.
+RTX_HD void qframe_of( const SceneDev& S, int32_t thing, int32_t tslot, float u, float v, const f3& o, const f3& d, float tmin, Frame& fr, o8& mat ) {
+	const char* ts = reinterpret_cast<const char*>( S.shade+thing ) ;
+	const o8 X0 = ldo_rec( ts ), X1 = ldo_rec( ts+32 ), X2 = ldo_rec( ts+64 ) ;
+	mat = ldo_rec( ts+96 ) ;
+	const double m0 = dbl( X0.a.x, X0.a.y ), m3 = dbl( X0.b.z, X0.b.w ), m5 = dbl( X1.a.z, X1.a.w ), m7 = dbl( X1.b.z, X1.b.w ), m10 = dbl( X2.b.x, X2.b.y ), m11 = dbl( X2.b.z, X2.b.w ) ;
+	const d3 dw = wide( d ) ;
+	const d3 center = mk3( m3, m7, m11 ) ;
+	if ( tslot<0 ) {
+		const double r = m0 ;
+		double td = 0. ;
+		sphere_root( center, r, wide( o ), dw, double( tmin ), td ) ;
+		const d3 pp = wide( o )+td*dw ;
+		const d3 outward = ( 1./r )*( pp-center ) ;
+		fr.p = narrow( pp ) ;
+		fr.facing = 0.>dot( dw, outward ) ;
+		fr.normal = narrow( fr.facing ? outward : -outward ) ;
+		return ;
+	}
+	// the three vertices as uploaded ride in the triangle record the traversal tested
+#if defined( __CUDA_ARCH__ )
+	const o8 D = ldo_rec( reinterpret_cast<const char*>( S.trav+thing )+96 ) ;
+	const q4* tris = reinterpret_cast<const q4*>( ( unsigned long long )__float_as_uint( D.a.z )|( ( unsigned long long )__float_as_uint( D.a.w )<<32 ) ) ;
+#else
+	const q4* tris = S.trav[thing].tris ;
+#endif
+	const q4* T = tris+size_t( tslot )*RTX_TRI_RECS ;
+	const o8 t01 = ldo_tri( T ), t23 = ldo_tri( T+2 ) ;
+	const q4 t0 = t01.a, t1 = t01.b, t2 = t23.a, t3 = t23.b ;
+	const d3 a = mk3( double( t0.x ), double( t0.y ), double( t0.z ) ) ;
+	const d3 b = mk3( double( t1.w ), double( t2.w ), double( t3.x ) ) ;
+	const d3 c = mk3( double( t3.y ), double( t3.z ), double( t3.w ) ) ;
+	d3 A, B, C ;
+	if ( asint( mat.b.w ) ) {
+		A = xfpoint_diag( m0, m3, m5, m7, m10, m11, a ) ;
+		B = xfpoint_diag( m0, m3, m5, m7, m10, m11, b ) ;
+		C = xfpoint_diag( m0, m3, m5, m7, m10, m11, c ) ;
+	} else {
+		double m[12] ;
+		m[0] = m0 ; m[1] = dbl( X0.a.z, X0.a.w ) ; m[2] = dbl( X0.b.x, X0.b.y ) ; m[3] = m3 ;
+		m[4] = dbl( X1.a.x, X1.a.y ) ; m[5] = m5 ; m[6] = dbl( X1.b.x, X1.b.y ) ; m[7] = m7 ;
+		m[8] = dbl( X2.a.x, X2.a.y ) ; m[9] = dbl( X2.a.z, X2.a.w ) ; m[10] = m10 ; m[11] = m11 ;
+		A = xfpoint( m, a ) ; B = xfpoint( m, b ) ; C = xfpoint( m, c ) ;
+	}
+	const float w = 1.f-u-v ;
+	const d3 pp = double( w )*A+double( u )*B+double( v )*C ;
+	d3 N = unitV( cross( B-A, C-A ) ) ;
+	if ( dot( dw, N )>0. )
+		N = -N ;
+	fr.p = narrow( pp ) ;
+	fr.normal = narrow( N ) ;
+	fr.facing = 0.>dot( dw, pp-center ) ;
+}
+
+RTX_HD bool qscatter( const o8& mat, const f3& dir, const Frame& fr, Pcg& rng, f3& attened, f3& out, bool guard ) {
+	const int32_t type = asint( mat.b.y ) ;
+	if ( type != 2 ) {
+		const f3 s = rng.rndVin1sphere() ;
+		attened = mk3( mat.a.x, mat.a.y, mat.a.z ) ;
+		if ( type == 0 ) {
+			f3 dnew = fr.normal+unitV( s ) ;
+			if ( guard && fabsf( dnew.x )<1e-8f && fabsf( dnew.y )<1e-8f && fabsf( dnew.z )<1e-8f )   // util.h:8 kNear0 (optx/optics_i.cu:86 has no guard)
+				dnew = fr.normal ;
+			out = dnew ;
+			return true ;
+		}
+		const f3 r = reflect( unitV( dir ), fr.normal ) ;
+		out = r+mat.a.w*s ;
+		return dot( out, fr.normal )>0.f ;
+	}
+	const f3 d1V = unitV( dir ) ;
+	const float cos_theta = fminf( dot( -d1V, fr.normal ), 1.f ) ;
+	const float sin_theta = sqrtf( 1.f-cos_theta*cos_theta ) ;
+	const float index = mat.b.x ;
+	const float ratio = fr.facing ? 1.f/index : index ;
+	const bool cannot = ratio*sin_theta>1.f ;
+	if ( cannot || schlick( cos_theta, ratio )>rng.rnd() )
+		out = reflect( d1V, fr.normal ) ;
+	else
+		out = refract( d1V, fr.normal, ratio ) ;
+	attened = mk3( 1.f, 1.f, 1.f ) ;
+	return true ;
+}
+
 
 // rtow.cxx:45-48
 RTX_HD f3 sky( const f3& dir ) {

@@ -42,6 +42,10 @@ namespace rtx {
 #ifndef RTX_FAST_PUSH
 #define RTX_FAST_PUSH 1         // node step: the three pushes as predicated straight-line stores (RegPool::push3; r2: 681.1 -> 666.6 ms; all three: 648.7)
 #endif
+#ifndef RTX_SHADE_INLINE
+#define RTX_SHADE_INLINE 1      // shading frame and scattering inline on thing records fetched with 256-bit loads (rtx_core.cuh qframe_of / qscatter) instead of the
+                                // __noinline__ frame_of / scatter, whose structures travel through local memory (54 LDL/STL + 29 narrow LDG per segment in the r1 profile)
+#endif
 #ifndef RTX_PREFETCH
 #define RTX_PREFETCH 0          // L1 prefetches beyond the first line of the next leaf (bits: 1 its second line, 2 / 4 the second-nearest child when a leaf / a node)
 #endif
@@ -420,8 +424,16 @@ template <class P> RTX_HD int step_thing( P& p, int slot, const SceneDev& S ) {
 		cur = pop_next( p, slot, S, sp, level ) ;
 		return finish_step( p, slot, cur, sp, level ) ;
 	}
+#if RTX_SHADE_INLINE
+	const char* ttb = reinterpret_cast<const char*>( tt ) ;
+	const o8 A = ldo_rec( ttb ), D = ldo_rec( ttb+96 ) ;   // inv[0..3]; nodes, tris, kind, n_tris, diag, pad
+	const double m0 = dbl( A.a.x, A.a.y ), m1 = dbl( A.a.z, A.a.w ), m2 = dbl( A.b.x, A.b.y ), m3 = dbl( A.b.z, A.b.w ) ;
+	const int32_t tt_kind = asint( D.b.x ), tt_diag = asint( D.b.z ) ;
+#else
 	const double m0 = RTX_LDG( tt->inv+0 ), m1 = RTX_LDG( tt->inv+1 ), m2 = RTX_LDG( tt->inv+2 ), m3 = RTX_LDG( tt->inv+3 ) ;
-	if ( RTX_LDG( &tt->kind ) == 0 ) {
+	const int32_t tt_kind = RTX_LDG( &tt->kind ) ;
+#endif
+	if ( tt_kind == 0 ) {
 		double td ;
 		if ( sphere_root( mk3( m0, m1, m2 ), m3, wide( o ), wide( d ), double( 1e-3f ), td ) ) {
 			const float t = float( td ) ;
@@ -436,6 +448,21 @@ template <class P> RTX_HD int step_thing( P& p, int slot, const SceneDev& S ) {
 	}
 	// enter the mesh: object-space ray, origin in double carried as hi+lo
 	d3 od, ddd ;
+#if RTX_SHADE_INLINE
+	const o8 B = ldo_rec( ttb+32 ), C = ldo_rec( ttb+64 ) ;
+	if ( tt_diag ) {
+		const double m5 = dbl( B.a.z, B.a.w ), m7 = dbl( B.b.z, B.b.w ), m10 = dbl( C.b.x, C.b.y ), m11 = dbl( C.b.z, C.b.w ) ;
+		od = xfpoint_diag( m0, m3, m5, m7, m10, m11, wide( o ) ) ;
+		ddd = xfvec_diag( m0, m5, m10, wide( d ) ) ;
+	} else {
+		double m[12] ;
+		m[0] = m0 ; m[1] = m1 ; m[2] = m2 ; m[3] = m3 ;
+		m[4] = dbl( B.a.x, B.a.y ) ; m[5] = dbl( B.a.z, B.a.w ) ; m[6] = dbl( B.b.x, B.b.y ) ; m[7] = dbl( B.b.z, B.b.w ) ;
+		m[8] = dbl( C.a.x, C.a.y ) ; m[9] = dbl( C.a.z, C.a.w ) ; m[10] = dbl( C.b.x, C.b.y ) ; m[11] = dbl( C.b.z, C.b.w ) ;
+		od = xfpoint( m, wide( o ) ) ;
+		ddd = xfvec( m, wide( d ) ) ;
+	}
+#else
 	if ( RTX_LDG( &tt->diag ) ) {
 		const double m5 = RTX_LDG( tt->inv+5 ), m7 = RTX_LDG( tt->inv+7 ), m10 = RTX_LDG( tt->inv+10 ), m11 = RTX_LDG( tt->inv+11 ) ;
 		od = xfpoint_diag( m0, m3, m5, m7, m10, m11, wide( o ) ) ;
@@ -447,13 +474,18 @@ template <class P> RTX_HD int step_thing( P& p, int slot, const SceneDev& S ) {
 		od = xfpoint( m, wide( o ) ) ;
 		ddd = xfvec( m, wide( d ) ) ;
 	}
+#endif
 	const f3 ohi = narrow( od ) ;
 	const f3 olo = narrow( od-wide( ohi ) ) ;
 	const f3 dd  = narrow( ddd ) ;
 	const f3 idir = mk3( safe_rcp( dd.x ), safe_rcp( dd.y ), safe_rcp( dd.z ) ) ;
 	st3( p, F_HX, slot, ohi ) ; st3( p, F_LX, slot, olo ) ; st3( p, F_EX, slot, dd ) ;
 	st3( p, F_IX, slot, idir ) ; st3( p, F_QX, slot, mk3( ohi.x*idir.x, ohi.y*idir.y, ohi.z*idir.z ) ) ;
+#if RTX_SHADE_INLINE && defined( __CUDA_ARCH__ )
+	p.si( F_NODES0, slot, asint( D.a.x ) ) ; p.si( F_NODES0+1, slot, asint( D.a.y ) ) ; p.si( F_TRIS0, slot, asint( D.a.z ) ) ; p.si( F_TRIS0+1, slot, asint( D.a.w ) ) ;
+#else
 	stp( p, F_NODES0, slot, ldptr( &tt->nodes ) ) ; stp( p, F_TRIS0, slot, ldptr( &tt->tris ) ) ;
+#endif
 	p.si( F_LEVEL, slot, k ) ;
 	p.push( slot, sp, RTX_STK_RETURN, 0.f ) ;
 	return finish_step( p, slot, 0, sp, k ) ;
@@ -482,13 +514,21 @@ template <class P> RTX_HD int step_shade( P& p, int slot, const SceneDev& S, f3&
 	if ( depth_left == 0 && S.variant != RTX_SEM_RTWO_I )
 		return K_REGEN ;
 	Frame fr ;
-	frame_of( S, h, ori, dir, 1e-3f, fr ) ;
 	Pcg rng ;
 	rng.state = uint64_t( uint32_t( p.i( F_RNG0, slot ) ) )|( uint64_t( uint32_t( p.i( F_RNG1, slot ) ) )<<32 ) ;
 	f3 att, out ;
+#if RTX_SHADE_INLINE
+	o8 mat ;
+	qframe_of( S, h.thing, h.prim<0 ? -1 : h.slot, h.u, h.v, ori, dir, 1e-3f, fr, mat ) ;
+	const bool go = qscatter( mat, dir, fr, rng, att, out, S.variant == RTX_SEM_RTOW ) ;
+	const int32_t h_type = asint( mat.b.y ) ;
+#else
+	frame_of( S, h, ori, dir, 1e-3f, fr ) ;
 	const bool go = scatter( S.shade+h.thing, dir, fr, rng, att, out, S.variant == RTX_SEM_RTOW ) ;
+	const int32_t h_type = RTX_LDG( &( S.shade+h.thing )->type ) ;
+#endif
 	uint32_t meta2 = meta ;
-	if ( ! ( meta&256u ) && RTX_LDG( &( S.shade+h.thing )->type ) != 2 ) {
+	if ( ! ( meta&256u ) && h_type != 2 ) {
 		guide = true ; gnormal = fr.normal ; galbedo = att ;   // att = the thing's albedo for diffuse / reflect
 		meta2 |= 256u ;
 	}
