@@ -189,6 +189,8 @@ def count_worker(a):
     ctx.render(ctx.params(api.camera(aspratio=a.width / a.height), a.count_spp, a.depth, seed=a.seed))
     c = ctx.counters()
     c["segments"] = ctx.stats()["segments"]
+    fs = ctx.frame_stats()
+    c["lanes_per_step"], c["steps"], c["live_paths"], c["kernel"] = fs.get("lanes_per_step"), fs.get("steps"), fs.get("live_paths"), fs.get("kernel")
     ctx.close()
     print("COUNTED " + json.dumps(c), flush=True)
 
@@ -219,7 +221,9 @@ def counted_leg(a):
     return {"sample": "%dx%d, %d spp, instrumented build (one global atomic per event)" % (a.width, a.height, a.count_spp),
             "segments": c["segments"], "node_steps_per_segment": nodes, "leaf_steps_per_segment": leaves, "triangle_tests_per_segment": tris,
             "thing_visits_per_segment": things, ("culled_visits_per_segment" if a.mode == "mesh" else "sphere_tests_per_segment"): other,
-            "flop_per_segment": flop, "bytes_per_segment": byts}
+            "flop_per_segment": flop, "bytes_per_segment": byts,
+            "lanes_per_step": c.get("lanes_per_step"), "warp_steps_per_segment": {k: v / n for k, v in (c.get("steps") or {}).items()},
+            "live_paths_per_bounce": c.get("live_paths")}
 
 
 # ------------------------------------------------------------------------- clocks

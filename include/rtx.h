@@ -78,6 +78,27 @@ typedef struct {
 	uint64_t bytes_device ;     /* device memory held */
 } rtx_stats ;
 
+/* Per-frame figures of the last rtx_render* (the reference's recipe for these is an ncu run,
+ * optx/README.md:294-316; SURVEY.md 5 asks for them from the library).  Stage times are device
+ * times from CUDA events on the context's stream.  The scheduling figures come from the kernels'
+ * own counters and are filled by the instrumented build only (librtx_count.so; `counted` = 1):
+ * per step kind k (1 node, 2 leaf, 3 top-level leaf, 4 shading, 5 new path) the warp iterations that
+ * ran it and the lanes that took part -- lanes[k] / steps[k] is the SIMD utilisation ncu reports as
+ * smsp__thread_inst_executed_per_inst_executed, per kind -- and live_paths[b] = rays traced at
+ * bounce b (0 = primary; 63 = 63 and deeper), i.e. the paths still alive there. */
+typedef struct {
+	float    ms_frame ;          /* clears + path tracing + (multi-GPU) reduce + resolve */
+	float    ms_trace ;          /* the path-tracing kernel on the first device */
+	float    ms_reduce_resolve ; /* k_resolve, or the fused peer-memory reduce + resolve */
+	float    ms_postproc ;       /* the last rtx_postproc */
+	uint32_t n_devices ;
+	uint32_t kernel ;            /* 0: k_render (one ray per lane), 1: k_render_q (compacting ray pool) */
+	uint32_t counted ;           /* 1: the fields below are filled */
+	uint32_t pad ;
+	uint64_t steps[8], lanes[8] ;
+	uint64_t live_paths[64] ;
+} rtx_frame_stats ;
+
 /* buffers of rtx_read / rtx_device_ptr */
 enum {
 	RTX_BUF_ACCUM   = 0,  /* uint64[4*w*h]: fixed-point (2^-32) radiance sums r,g,b and segment count */
@@ -96,6 +117,16 @@ enum { RTX_PP_NONE = 0, RTX_PP_SRGB = 1 } ;
 
 /* cudaFree(0) + optixInit + optixDeviceContextCreate, optx/rtwo.cxx:115-128 */
 int  rtx_init( int device, rtx_ctx** out ) ;
+/* The same on several GPUs of one node (the reference is single-context, optx/rtwo.cxx:126-127; this
+ * is where a caller reaches the other devices).  The context returned stands for all of them: scene
+ * calls are repeated on every device (scene and hierarchies are replicated), rtx_render* splits the
+ * samples of a frame over the devices -- device r traces the global samples r, r+n, ... -- and one
+ * kernel on the first device sums the fixed-point accumulation buffers through peer memory (NVLink /
+ * NVSwitch; staged copies where two devices are not peers) and resolves the frame.  Integer sums:
+ * the frame equals the one-device frame bit for bit.  1 <= n_devices <= 8; a device may be named more
+ * than once (two replicas on one GPU: used by the tests on a single-GPU box). */
+int  rtx_init_multi( int n_devices, const int* device_ids, rtx_ctx** out ) ;
+int  rtx_device_count( const rtx_ctx* ctx ) ;
 void rtx_shutdown( rtx_ctx* ctx ) ;
 /* util_cpu.h:18-53 CUDA_CHECK/OPTX_CHECK text; ctx may be NULL for rtx_init failures */
 const char* rtx_last_error( const rtx_ctx* ctx ) ;
@@ -148,6 +179,8 @@ int rtx_write( rtx_ctx* ctx, int buffer, const void* host_src, size_t bytes ) ;
 
 /* the -S line of optx/rtwo.cxx:579-591 and more */
 int rtx_stats_get( rtx_ctx* ctx, rtx_stats* out ) ;
+/* stage times of the last frame; scheduling counters (instrumented build) since the last reset */
+int rtx_frame_stats_get( rtx_ctx* ctx, rtx_frame_stats* out, int reset ) ;
 /* measurement instrument: read bandwidth of a `bytes` buffer read `repeats` times by all SMs,
  * bypassing L1 -- the L2 read peak when the buffer fits L2 (SURVEY.md 8(d) asks for it measured
  * on the box), the HBM read peak when it is far larger.  No counterpart in the reference. */

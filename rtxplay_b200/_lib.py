@@ -33,13 +33,19 @@ class RtxStats(ctypes.Structure):
                 ("n_triangles_instanced", ctypes.c_uint64), ("bytes_device", ctypes.c_uint64)]
 
 
+class RtxFrameStats(ctypes.Structure):
+    _fields_ = [("ms_frame", ctypes.c_float), ("ms_trace", ctypes.c_float), ("ms_reduce_resolve", ctypes.c_float), ("ms_postproc", ctypes.c_float),
+                ("n_devices", ctypes.c_uint32), ("kernel", ctypes.c_uint32), ("counted", ctypes.c_uint32), ("pad", ctypes.c_uint32),
+                ("steps", ctypes.c_uint64 * 8), ("lanes", ctypes.c_uint64 * 8), ("live_paths", ctypes.c_uint64 * 64)]
+
+
 # every symbol include/rtx.h declares (tests check that the library exports all of them)
 SYMBOLS = [
-    "rtx_init", "rtx_shutdown", "rtx_last_error", "rtx_mesh_create", "rtx_sphere_create", "rtx_thing_add",
+    "rtx_init", "rtx_init_multi", "rtx_device_count", "rtx_shutdown", "rtx_last_error", "rtx_mesh_create", "rtx_sphere_create", "rtx_thing_add",
     "rtx_thing_set_xf", "rtx_thing_get_xf", "rtx_thing_set_optics", "rtx_accel_build", "rtx_accel_refit",
     "rtx_resize", "rtx_render", "rtx_render_accumulate", "rtx_resolve", "rtx_pick", "rtx_postproc",
     "rtx_postproc_dev", "rtx_primary_hits", "rtx_trace_rays", "rtx_read", "rtx_device_ptr", "rtx_write",
-    "rtx_stats_get", "rtx_probe_read", "rtx_build_stages", "rtx_last_render_ms", "rtx_counters_get", "rtx_camera_set", "rtx_sphere_mesh",
+    "rtx_stats_get", "rtx_frame_stats_get", "rtx_probe_read", "rtx_build_stages", "rtx_last_render_ms", "rtx_counters_get", "rtx_camera_set", "rtx_sphere_mesh",
 ]
 
 

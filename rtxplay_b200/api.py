@@ -9,7 +9,7 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from ._lib import RtxCamera, RtxOptics, RtxParams, RtxStats
+from ._lib import RtxCamera, RtxFrameStats, RtxOptics, RtxParams, RtxStats
 
 DIFFUSE, REFLECT, REFRACT = 0, 1, 2
 BUF_ACCUM, BUF_RAWRGB, BUF_RPP, BUF_IMAGE, BUF_HIT_ID, BUF_HIT_T, BUF_NORMALS, BUF_ALBEDOS, BUF_PICK_ID, BUF_GUIDE_ACC = range(10)
@@ -61,12 +61,22 @@ def sphere_mesh(radius=1., ndiv=6):
 
 
 class Context:
-    def __init__(self, device=0):
+    def __init__(self, device=0, devices=None):
+        """devices: a list of CUDA device indices -> one context over all of them (rtx_init_multi):
+        the scene is replicated, a frame's samples are split, the sums reduced on the first device."""
         self._L = _lib.lib()
         self._c = ctypes.c_void_p()
-        if self._L.rtx_init(ctypes.c_int(device), ctypes.byref(self._c)):
+        if devices is None:
+            rc = self._L.rtx_init(ctypes.c_int(device), ctypes.byref(self._c))
+        else:
+            ids = (ctypes.c_int * len(devices))(*[int(d) for d in devices])
+            rc = self._L.rtx_init_multi(ctypes.c_int(len(devices)), ids, ctypes.byref(self._c))
+        if rc:
             raise RtxError(self._L.rtx_last_error(None).decode())
         self.w = self.h = 0
+
+    def device_count(self):
+        return int(self._L.rtx_device_count(self._c))
 
     def close(self):
         if self._c:
@@ -217,6 +227,23 @@ class Context:
         b, t = (ctypes.c_float * 5)(), (ctypes.c_float * 5)()
         self._ck(self._L.rtx_build_stages(self._c, b, t))
         return dict(zip(self.BUILD_STAGES, [float(v) for v in b])), dict(zip(self.BUILD_STAGES, [float(v) for v in t]))
+
+    STEP_KINDS = ("", "node", "leaf", "thing", "shade", "regen")
+
+    def frame_stats(self, reset=True):
+        """Stage times of the last frame; with the instrumented build also warp iterations / lanes per
+        step kind and the paths alive per bounce (rtx_frame_stats of include/rtx.h)."""
+        f = RtxFrameStats()
+        self._ck(self._L.rtx_frame_stats_get(self._c, ctypes.byref(f), ctypes.c_int(1 if reset else 0)))
+        out = {k: getattr(f, k) for k in ("ms_frame", "ms_trace", "ms_reduce_resolve", "ms_postproc", "n_devices", "kernel", "counted")}
+        if f.counted:
+            out["steps"] = {self.STEP_KINDS[k]: int(f.steps[k]) for k in range(1, 6)}
+            out["lanes_per_step"] = {self.STEP_KINDS[k]: (f.lanes[k] / f.steps[k] if f.steps[k] else 0.) for k in range(1, 6)}
+            live = [int(v) for v in f.live_paths]
+            while live and live[-1] == 0:
+                live.pop()
+            out["live_paths"] = live
+        return out
 
     def stats(self):
         s = RtxStats()

@@ -89,7 +89,8 @@ struct rtx_ctx {
 	std::string  err ;
 	cudaStream_t stream = nullptr ;
 	cudaMemPool_t pool = nullptr ;   // build workspace and hierarchies (talloc)
-	cudaEvent_t  ev0 = nullptr, ev1 = nullptr ;
+	cudaEvent_t  ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev_in = nullptr ;   // frame: before the kernel, behind it, behind the resolve; start of the call
+	float        ms_frame = 0.f, ms_resolve = 0.f, ms_postproc = 0.f ;
 
 	std::vector<Mesh>      meshes ;
 	std::vector<ThingHost> things ;
@@ -126,6 +127,14 @@ struct rtx_ctx {
 	uint32_t* d_tile_counter = nullptr ;
 	int32_t*  d_ovf = nullptr ;      // overflow stacks of the resident render warps
 	uint32_t  render_grid = 0 ;
+	// multi-GPU (rtx_init_multi): the context the caller holds is the root; its replicas, one per
+	// further device, receive every scene call, render their share of the samples, and the root
+	// sums their accumulation buffers through peer memory (k_reduce_resolve)
+	std::vector<rtx_ctx*> replicas ;
+	cudaEvent_t ev_done = nullptr ;           // a replica's frame kernel has finished (the root's stream waits on it)
+	std::vector<uint64_t*>  stage_accum ;     // root-side copies of replica buffers where peer access is not available
+	std::vector<long long*> stage_guide ;
+	std::vector<char>       peer_ok ;         // per replica: the root reads its memory directly
 	int       kernel = RTX_DEFAULT_KERNEL ;   // which path-tracing kernel do_render launches
 	uint32_t  q_grid = 0 ;           // k_render_q: resident warps, their cold ray records and overflow stacks
 	q4*       d_qcold = nullptr ;
@@ -432,11 +441,15 @@ void do_resolve( rtx_ctx* c, uint64_t total_spp ) {
 	CK( cudaGetLastError() ) ;
 }
 
-void do_render( rtx_ctx* c, const rtx_params* p, bool resolve ) {
+__global__ void k_sum_segments( const uint64_t* accum, uint32_t npix, unsigned long long* out ) ;
+
+// the asynchronous part of a frame on one context: buffers cleared, the path-tracing kernel
+// launched on the context's stream, its fault word fetched behind it
+void launch_render( rtx_ctx* c, const rtx_params* p ) {
+	CK( cudaSetDevice( c->device ) ) ;
 	FrameArgs a = frame_args( c, p ) ;
 	unit_plan( a ) ;
 	c->guides_valid = a.guides != 0 ;
-	CK( cudaEventRecord( c->ev0, c->stream ) ) ;
 	if ( a.depth>255u ) throw std::runtime_error( "rtx: depth above 255 is not supported" ) ;
 	if ( a.spp == 0 ) throw std::runtime_error( "rtx: spp must be at least 1" ) ;
 	const uint32_t n_tiles = ( ( a.w+RTX_TILE_W-1u )>>RTX_TILE_WLOG )*( ( a.h+RTX_TILE_H-1u )>>RTX_TILE_HLOG )*( a.chunks_full+a.chunks_taper ) ;   // work units
@@ -456,14 +469,107 @@ void do_render( rtx_ctx* c, const rtx_params* p, bool resolve ) {
 	else            k_render<false><<<min( c->render_grid, n_tiles ), 32, 0, c->stream>>>( a, c->d_tile_counter, c->d_ovf ) ;
 	c->launches += 1 ;
 	CK( cudaGetLastError() ) ;
-	CK( cudaEventRecord( c->ev1, c->stream ) ) ;
 	fault_fetch( c ) ;
-	if ( resolve )
-		do_resolve( c, p->spp ) ;
+}
+
+void do_render( rtx_ctx* c, const rtx_params* p, bool resolve ) {
+	const uint32_t G = 1u+uint32_t( c->replicas.size() ) ;
+	CK( cudaSetDevice( c->device ) ) ;
+	CK( cudaEventRecord( c->ev0, c->stream ) ) ;
+	if ( G == 1u ) {
+		launch_render( c, p ) ;
+		CK( cudaEventRecord( c->ev1, c->stream ) ) ;
+		if ( resolve )
+			do_resolve( c, p->spp ) ;
+		CK( cudaEventRecord( c->ev2, c->stream ) ) ;
+		CK( cudaStreamSynchronize( c->stream ) ) ;
+		CK( cudaEventElapsedTime( &c->ms_render, c->ev0, c->ev1 ) ) ;
+		CK( cudaEventElapsedTime( &c->ms_resolve, c->ev1, c->ev2 ) ) ;
+		CK( cudaEventElapsedTime( &c->ms_frame, c->ev0, c->ev2 ) ) ;
+		c->paths = uint64_t( p->image_w )*p->image_h*p->spp ;
+		fault_check( c, "rtx_render" ) ;
+		return ;
+	}
+	// samples split over the devices: device r traces the global samples sample0 + (r + k G) stride
+	// (BASELINE.json north_star).  The sums are integers, so the frame does not depend on G.
+	const uint32_t stride = p->sample_stride ? p->sample_stride : 1u ;
+	PeerBufs pb ;
+	memset( &pb, 0, sizeof( pb ) ) ;
+	pb.n = int( G ) ;
+	pb.accum[0] = c->d_accum ;
+	for ( uint32_t r = 0 ; r<G ; r++ ) {
+		rtx_ctx* d = r ? c->replicas[r-1] : c ;
+		rtx_params q = *p ;
+		q.spp = p->spp/G+( r<p->spp%G ? 1u : 0u ) ;
+		q.sample0 = p->sample0+r*stride ;
+		q.sample_stride = stride*G ;
+		if ( r ) q.accumulate = 0 ;   // (the root's buffer carries what was accumulated before; replicas hold this call's share only)
+		if ( q.spp ) launch_render( d, &q ) ;
+		else if ( r ) {
+			CK( cudaSetDevice( d->device ) ) ;
+			CK( cudaMemsetAsync( d->d_accum, 0, sizeof( uint64_t )*4*size_t( d->w )*d->h, d->stream ) ) ;
+			if ( p->guides && d->d_guide_acc ) CK( cudaMemsetAsync( d->d_guide_acc, 0, sizeof( long long )*6*size_t( d->w )*d->h, d->stream ) ) ;
+		}
+		if ( r == 0 ) { CK( cudaSetDevice( c->device ) ) ; CK( cudaEventRecord( c->ev_in, c->stream ) ) ; }   // behind the root's own kernel
+		if ( r ) {
+			CK( cudaSetDevice( d->device ) ) ;
+			const size_t np = size_t( d->w )*d->h ;
+			if ( c->peer_ok[r-1] ) {
+				pb.accum[r] = d->d_accum ; pb.guide[r] = p->guides ? d->d_guide_acc : nullptr ;
+			} else {
+				// no peer access between the two devices: the replica's sums travel through a copy on the root
+				CK( cudaMemcpyPeerAsync( c->stage_accum[r-1], c->device, d->d_accum, d->device, sizeof( uint64_t )*4*np, d->stream ) ) ;
+				pb.accum[r] = c->stage_accum[r-1] ;
+				if ( p->guides ) {
+					if ( ! c->stage_guide[r-1] ) { CK( cudaSetDevice( c->device ) ) ; c->stage_guide[r-1] = dalloc<long long>( c, 6*np ) ; CK( cudaSetDevice( d->device ) ) ; }
+					CK( cudaMemcpyPeerAsync( c->stage_guide[r-1], c->device, d->d_guide_acc, d->device, sizeof( long long )*6*np, d->stream ) ) ;
+					pb.guide[r] = c->stage_guide[r-1] ;
+				}
+			}
+			CK( cudaEventRecord( d->ev_done, d->stream ) ) ;
+		}
+	}
+	CK( cudaSetDevice( c->device ) ) ;
+	pb.guide[0] = p->guides ? c->d_guide_acc : nullptr ;
+	c->guides_valid = p->guides != 0 ;
+	for ( rtx_ctx* d : c->replicas ) CK( cudaStreamWaitEvent( c->stream, d->ev_done, 0 ) ) ;
+	if ( getenv( "RTX_DEBUG_MULTI" ) ) {
+		// development aid: the segment sums of every device's buffer before the reduce
+		for ( uint32_t r = 0 ; r<G ; r++ ) {
+			rtx_ctx* d = r ? c->replicas[r-1] : c ;
+			CK( cudaSetDevice( d->device ) ) ;
+			CK( cudaStreamSynchronize( d->stream ) ) ;
+			CK( cudaMemsetAsync( d->d_counter, 0, sizeof( unsigned long long ), d->stream ) ) ;
+			k_sum_segments<<<64, 256, 0, d->stream>>>( d->d_accum, d->w*d->h, d->d_counter ) ;
+			unsigned long long sg = 0 ;
+			CK( cudaMemcpyAsync( &sg, d->d_counter, sizeof( sg ), cudaMemcpyDeviceToHost, d->stream ) ) ;
+			CK( cudaStreamSynchronize( d->stream ) ) ;
+			fprintf( stderr, "rtx multi: device slot %u (device %d): %llu segments in %p, pb.accum %p; %ux%u, grid %u, %u things, built %d, fault %u\n", r, d->device, sg, ( void* ) d->d_accum, ( const void* ) pb.accum[r],
+				d->w, d->h, d->render_grid, d->n_things_dev, int( d->built ), *d->h_fault ) ;
+		}
+		CK( cudaSetDevice( c->device ) ) ;
+	}
+	// one kernel on the root: sum of the devices' buffers read over NVLink peer memory, written back as
+	// the root's accumulation buffer, and (rtx_render) the mean + clamp of optx/camera_i.cu:105 behind it
+	const uint32_t np = c->w*c->h ;
+	CK( cudaEventRecord( c->ev2, c->stream ) ) ;
+	k_reduce_resolve<<<( np+255 )/256, 256, 0, c->stream>>>( pb, c->d_accum, np, p->spp ? p->spp : 1, resolve ? 1 : 0, c->d_raw, c->d_rpp,
+		p->guides ? c->d_guide_acc : nullptr, c->d_normals, c->d_albedos ) ;
+	c->launches += 1 ;
+	CK( cudaGetLastError() ) ;
+	CK( cudaEventRecord( c->ev1, c->stream ) ) ;
 	CK( cudaStreamSynchronize( c->stream ) ) ;
-	CK( cudaEventElapsedTime( &c->ms_render, c->ev0, c->ev1 ) ) ;
-	c->paths = uint64_t( a.w )*a.h*a.spp ;
+	for ( rtx_ctx* d : c->replicas ) { CK( cudaSetDevice( d->device ) ) ; CK( cudaStreamSynchronize( d->stream ) ) ; }
+	CK( cudaSetDevice( c->device ) ) ;
+	CK( cudaEventElapsedTime( &c->ms_render, c->ev0, c->ev_in ) ) ;
+	CK( cudaEventElapsedTime( &c->ms_resolve, c->ev2, c->ev1 ) ) ;
+	CK( cudaEventElapsedTime( &c->ms_frame, c->ev0, c->ev1 ) ) ;
+	c->paths = uint64_t( p->image_w )*p->image_h*p->spp ;
 	fault_check( c, "rtx_render" ) ;
+	for ( rtx_ctx* d : c->replicas ) {
+		try { fault_check( d, "rtx_render" ) ; }
+		catch ( ... ) { CK( cudaSetDevice( c->device ) ) ; throw ; }
+	}
 }
 
 struct BufInfo { void* ptr ; size_t bytes ; } ;
@@ -496,6 +602,8 @@ __global__ void __launch_bounds__( 256 ) k_sum_segments( const uint64_t* accum, 
 
 } // namespace
 
+// multi-GPU: a scene call made on the root is repeated on every replica (same arguments, same ids)
+#define RTX_FANOUT( c, call ) do { for ( rtx_ctx* r_ : ( c )->replicas ) { if ( call ) { ( c )->err = "replica on device "+std::to_string( r_->device )+": "+r_->err ; cudaSetDevice( ( c )->device ) ; return 1 ; } } if ( ! ( c )->replicas.empty() ) cudaSetDevice( ( c )->device ) ; } while ( 0 )
 #define RTX_TRY( c ) try {
 #define RTX_END( c ) return 0 ; } catch ( const std::exception& e_ ) { if ( c ) ( c )->err = e_.what() ; else g_init_error = e_.what() ; cudaGetLastError() ; return 1 ; }
 
@@ -518,7 +626,7 @@ int rtx_init( int device, rtx_ctx** out ) {
 		c = new rtx_ctx ;
 		c->device = device ;
 		CK( cudaStreamCreateWithFlags( &c->stream, cudaStreamNonBlocking ) ) ;
-		CK( cudaEventCreate( &c->ev0 ) ) ; CK( cudaEventCreate( &c->ev1 ) ) ;
+		CK( cudaEventCreate( &c->ev0 ) ) ; CK( cudaEventCreate( &c->ev1 ) ) ; CK( cudaEventCreate( &c->ev2 ) ) ; CK( cudaEventCreate( &c->ev_in ) ) ;
 		for ( cudaEvent_t& e : c->stage_ev ) CK( cudaEventCreate( &e ) ) ;
 		{
 			cudaMemPoolProps pp ;
@@ -595,8 +703,58 @@ int rtx_init( int device, rtx_ctx** out ) {
 	}
 }
 
+int rtx_init_multi( int n_devices, const int* device_ids, rtx_ctx** out ) {
+	if ( n_devices<1 || n_devices>RTX_MAX_DEVICES || ! device_ids ) { g_init_error = "rtx_init_multi: 1 to 8 devices" ; return 1 ; }
+	rtx_ctx* root = nullptr ;
+	if ( rtx_init( device_ids[0], &root ) )
+		return 1 ;
+	try {
+		for ( int k = 1 ; k<n_devices ; k++ ) {
+			rtx_ctx* r = nullptr ;
+			if ( rtx_init( device_ids[k], &r ) )
+				throw std::runtime_error( g_init_error ) ;
+			r->kernel = root->kernel ;
+			CK( cudaEventCreateWithFlags( &r->ev_done, cudaEventDisableTiming ) ) ;
+			root->replicas.push_back( r ) ;
+			// the root reads the replica's buffers directly where the devices are peers (NVLink / NVSwitch
+			// on a B200 board; trivially so for a second context on the same device)
+			int ok = r->device == root->device ? 1 : 0 ;
+			if ( ! ok ) {
+				CK( cudaDeviceCanAccessPeer( &ok, root->device, r->device ) ) ;
+				if ( ok ) {
+					CK( cudaSetDevice( root->device ) ) ;
+					const cudaError_t e = cudaDeviceEnablePeerAccess( r->device, 0 ) ;
+					if ( e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled ) ok = 0 ;
+					cudaGetLastError() ;
+				}
+			}
+			root->peer_ok.push_back( char( ok ) ) ;
+			root->stage_accum.push_back( nullptr ) ; root->stage_guide.push_back( nullptr ) ;
+			if ( getenv( "RTX_VERBOSE" ) ) fprintf( stderr, "rtx_init_multi: replica %d on device %d, %s\n", k, r->device, ok ? "peer access" : "staged copies" ) ;
+		}
+		CK( cudaSetDevice( root->device ) ) ;
+	} catch ( const std::exception& e ) {
+		g_init_error = e.what() ;
+		rtx_shutdown( root ) ;
+		cudaGetLastError() ;
+		return 1 ;
+	}
+	*out = root ;
+	return 0 ;
+}
+
+int rtx_device_count( const rtx_ctx* c ) { return c ? 1+int( c->replicas.size() ) : 0 ; }
+
 void rtx_shutdown( rtx_ctx* c ) {
 	if ( ! c ) return ;
+	for ( rtx_ctx* r : c->replicas ) rtx_shutdown( r ) ;
+	c->replicas.clear() ;
+	cudaSetDevice( c->device ) ;
+	for ( size_t k = 0 ; k<c->stage_accum.size() ; k++ ) {
+		const size_t np = size_t( c->w )*c->h ;
+		dfree( c, c->stage_accum[k], 4*np ) ; dfree( c, c->stage_guide[k], 6*np ) ;
+	}
+	if ( c->ev_done ) cudaEventDestroy( c->ev_done ) ;
 	cudaSetDevice( c->device ) ;
 	cudaStreamSynchronize( c->stream ) ;
 	for ( Mesh& m : c->meshes ) {
@@ -612,7 +770,7 @@ void rtx_shutdown( rtx_ctx* c ) {
 	dfree( c, c->d_counter, 1 ) ; dfree( c, c->d_tile_counter, 2+2*256 ) ;
 	dfree( c, c->d_ovf, size_t( c->render_grid )*RTX_POOL_R*RTX_POOL_OVF*2 ) ;
 	dfree( c, c->d_qcold, size_t( c->q_grid )*RTX_QR*4 ) ; dfree( c, c->d_qovf, size_t( c->q_grid )*RTX_QR*RTX_QOVF*2 ) ;
-	cudaEventDestroy( c->ev0 ) ; cudaEventDestroy( c->ev1 ) ;
+	cudaEventDestroy( c->ev0 ) ; cudaEventDestroy( c->ev1 ) ; if ( c->ev2 ) cudaEventDestroy( c->ev2 ) ; if ( c->ev_in ) cudaEventDestroy( c->ev_in ) ;
 	for ( cudaEvent_t e : c->stage_ev ) if ( e ) cudaEventDestroy( e ) ;
 	cudaStreamSynchronize( c->stream ) ;   // the stream-ordered frees above
 	if ( c->pool ) cudaMemPoolDestroy( c->pool ) ;
@@ -662,6 +820,7 @@ int rtx_mesh_create( rtx_ctx* c, const float* xyz, uint32_t nv, const uint32_t* 
 	tfree( c, plo, nt ) ; tfree( c, phi, nt ) ;
 	*mesh_id = uint32_t( c->meshes.size() ) ;
 	c->meshes.push_back( m ) ;
+	RTX_FANOUT( c, [&]{ uint32_t id_ ; return rtx_mesh_create( r_, xyz, nv, idx, nt, &id_ ) ; }() ) ;
 	RTX_END( c )
 }
 
@@ -671,6 +830,7 @@ int rtx_sphere_create( rtx_ctx* c, uint32_t* mesh_id ) {
 	m.analytic = true ;
 	*mesh_id = uint32_t( c->meshes.size() ) ;
 	c->meshes.push_back( m ) ;
+	RTX_FANOUT( c, [&]{ uint32_t id_ ; return rtx_sphere_create( r_, &id_ ) ; }() ) ;
 	RTX_END( c )
 }
 
@@ -685,6 +845,7 @@ int rtx_thing_add( rtx_ctx* c, uint32_t mesh_id, const rtx_optics* optics, uint3
 	memcpy( th.xf, ident, sizeof( ident ) ) ;
 	*thing_id = uint32_t( c->things.size() ) ;
 	c->things.push_back( th ) ;
+	RTX_FANOUT( c, [&]{ uint32_t id_ ; return rtx_thing_add( r_, mesh_id, optics, &id_ ) ; }() ) ;
 	RTX_END( c )
 }
 
@@ -692,6 +853,7 @@ int rtx_thing_set_xf( rtx_ctx* c, uint32_t thing_id, const float xf[12] ) {
 	RTX_TRY( c )
 	if ( thing_id>=c->things.size() ) throw std::runtime_error( "rtx_thing_set_xf: unknown thing" ) ;
 	memcpy( c->things[thing_id].xf, xf, sizeof( float )*12 ) ;
+	RTX_FANOUT( c, rtx_thing_set_xf( r_, thing_id, xf ) ) ;
 	RTX_END( c )
 }
 
@@ -707,6 +869,7 @@ int rtx_thing_set_optics( rtx_ctx* c, uint32_t thing_id, const rtx_optics* optic
 	if ( thing_id>=c->things.size() ) throw std::runtime_error( "rtx_thing_set_optics: unknown thing" ) ;
 	if ( optics->type<0 || optics->type>2 ) throw std::runtime_error( "rtx_thing_set_optics: unknown optics type" ) ;
 	c->things[thing_id].optics = *optics ;
+	RTX_FANOUT( c, rtx_thing_set_optics( r_, thing_id, optics ) ) ;
 	RTX_END( c )
 }
 
@@ -723,6 +886,7 @@ int rtx_accel_build( rtx_ctx* c ) {
 	CK( cudaEventElapsedTime( &c->ms_tlas, c->ev0, c->ev1 ) ) ;
 	if ( n ) stage_collect( c, c->ms_stage_tlas, false ) ;
 	c->built = true ;
+	RTX_FANOUT( c, rtx_accel_build( r_ ) ) ;
 	RTX_END( c )
 }
 
@@ -738,6 +902,7 @@ int rtx_accel_refit( rtx_ctx* c ) {
 	CK( cudaStreamSynchronize( c->stream ) ) ;
 	CK( cudaEventElapsedTime( &c->ms_tlas, c->ev0, c->ev1 ) ) ;
 	if ( c->tlas.n ) stage_collect( c, c->ms_stage_tlas, false ) ;
+	RTX_FANOUT( c, rtx_accel_refit( r_ ) ) ;
 	RTX_END( c )
 }
 
@@ -745,6 +910,7 @@ int rtx_resize( rtx_ctx* c, uint32_t w, uint32_t h ) {
 	RTX_TRY( c )
 	CK( cudaSetDevice( c->device ) ) ;
 	if ( w == 0 || h == 0 || uint64_t( w )*h>=( 1ull<<31 ) ) throw std::runtime_error( "rtx_resize: bad image size" ) ;
+	for ( size_t k = 0 ; k<c->stage_accum.size() ; k++ ) { dfree( c, c->stage_accum[k], 4*size_t( c->w )*c->h ) ; dfree( c, c->stage_guide[k], 6*size_t( c->w )*c->h ) ; }
 	free_frame( c ) ;
 	c->w = w ; c->h = h ;
 	const size_t np = size_t( w )*h ;
@@ -756,7 +922,9 @@ int rtx_resize( rtx_ctx* c, uint32_t w, uint32_t h ) {
 	CK( cudaMemsetAsync( c->d_rpp, 0, np*sizeof( uint32_t ), c->stream ) ) ;
 	CK( cudaMemsetAsync( c->d_normals, 0, 3*np*sizeof( float ), c->stream ) ) ;
 	CK( cudaMemsetAsync( c->d_albedos, 0, 3*np*sizeof( float ), c->stream ) ) ;
+	for ( size_t k = 0 ; k<c->replicas.size() ; k++ ) if ( ! c->peer_ok[k] ) c->stage_accum[k] = dalloc<uint64_t>( c, 4*np ) ;
 	CK( cudaStreamSynchronize( c->stream ) ) ;
+	RTX_FANOUT( c, rtx_resize( r_, w, h ) ) ;
 	RTX_END( c )
 }
 
@@ -805,10 +973,13 @@ int rtx_postproc( rtx_ctx* c, int kind ) {
 	if ( c->w == 0 ) throw std::runtime_error( "rtx_postproc: no frame (call rtx_resize)" ) ;
 	if ( kind != RTX_PP_NONE && kind != RTX_PP_SRGB ) throw std::runtime_error( "rtx_postproc: unknown kind" ) ;
 	const uint32_t np = c->w*c->h ;
+	CK( cudaEventRecord( c->ev2, c->stream ) ) ;
 	k_postproc<<<( np+255 )/256, 256, 0, c->stream>>>( c->d_raw, c->d_image, np, kind == RTX_PP_SRGB ) ;
 	c->launches += 1 ;
 	CK( cudaGetLastError() ) ;
+	CK( cudaEventRecord( c->ev_in, c->stream ) ) ;
 	CK( cudaStreamSynchronize( c->stream ) ) ;
+	CK( cudaEventElapsedTime( &c->ms_postproc, c->ev2, c->ev_in ) ) ;
 	RTX_END( c )
 }
 
@@ -909,6 +1080,37 @@ int rtx_stats_get( rtx_ctx* c, rtx_stats* out ) {
 	for ( const Mesh& m : c->meshes ) out->n_triangles += m.nt ;
 	for ( const ThingHost& t : c->things ) out->n_triangles_instanced += c->meshes[t.mesh].nt ;
 	out->bytes_device = c->bytes ;
+	RTX_END( c )
+}
+
+int rtx_frame_stats_get( rtx_ctx* c, rtx_frame_stats* out, int reset ) {
+	RTX_TRY( c )
+	CK( cudaSetDevice( c->device ) ) ;
+	memset( out, 0, sizeof( *out ) ) ;
+	out->ms_frame = c->ms_frame ; out->ms_trace = c->ms_render ; out->ms_reduce_resolve = c->ms_resolve ; out->ms_postproc = c->ms_postproc ;
+	out->n_devices = 1u+uint32_t( c->replicas.size() ) ;
+	out->kernel = uint32_t( c->kernel ) ;
+#if defined( RTX_DEVICE_COUNTERS )
+	// (the counters of every device replica live in that device's copy of the symbols)
+	out->counted = 1 ;
+	CK( cudaStreamSynchronize( c->stream ) ) ;
+	for ( uint32_t r = 0 ; r<out->n_devices ; r++ ) {
+		rtx_ctx* d = r ? c->replicas[r-1] : c ;
+		if ( r && d->device == c->device ) continue ;   // same device, same symbols
+		CK( cudaSetDevice( d->device ) ) ;
+		unsigned long long st[8], ln[8], lv[64] ;
+		CK( cudaMemcpyFromSymbol( st, g_dev_steps, sizeof( st ) ) ) ; CK( cudaMemcpyFromSymbol( ln, g_dev_lanes, sizeof( ln ) ) ) ; CK( cudaMemcpyFromSymbol( lv, g_dev_live, sizeof( lv ) ) ) ;
+		for ( int k = 0 ; k<8 ; k++ ) { out->steps[k] += st[k] ; out->lanes[k] += ln[k] ; }
+		for ( int k = 0 ; k<64 ; k++ ) out->live_paths[k] += lv[k] ;
+		if ( reset ) {
+			memset( st, 0, sizeof( st ) ) ; memset( lv, 0, sizeof( lv ) ) ;
+			CK( cudaMemcpyToSymbol( g_dev_steps, st, sizeof( st ) ) ) ; CK( cudaMemcpyToSymbol( g_dev_lanes, st, sizeof( st ) ) ) ; CK( cudaMemcpyToSymbol( g_dev_live, lv, sizeof( lv ) ) ) ;
+		}
+	}
+	CK( cudaSetDevice( c->device ) ) ;
+#else
+	( void ) reset ;
+#endif
 	RTX_END( c )
 }
 

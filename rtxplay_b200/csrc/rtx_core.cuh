@@ -44,7 +44,9 @@
 #endif
 
 #if defined( RTX_DEVICE_COUNTERS ) && defined( __CUDACC__ )
-namespace rtx { enum { DC_rays, DC_nodes, DC_leaves, DC_tris, DC_things, DC_spheres, DC_enters, DC_N } ; __device__ unsigned long long g_dev_counts[DC_N] ; }   // (librtx has one CUDA translation unit)
+namespace rtx { enum { DC_rays, DC_nodes, DC_leaves, DC_tris, DC_things, DC_spheres, DC_enters, DC_N } ; __device__ unsigned long long g_dev_counts[DC_N] ;   // (librtx has one CUDA translation unit)
+	// scheduling statistics of the render kernels: warp iterations and lane-steps per step kind, paths alive per bounce
+	__device__ unsigned long long g_dev_steps[8], g_dev_lanes[8], g_dev_live[64] ; }
 #endif
 // traversal statistics for the host harness (compiled out of the product)
 #if defined( RTX_STATS )
@@ -65,6 +67,15 @@ namespace rtx { void trace_event( char c ) ; }
 #define RTX_EVENT( c ) ( ( void ) 0 )
 #define RTX_COUNT( f ) ( ( void ) 0 )
 #define RTX_COUNT_MAX( f, v ) ( ( void ) 0 )
+#endif
+#if defined( RTX_DEVICE_COUNTERS ) && defined( __CUDA_ARCH__ )
+// one warp iteration of step kind k with `mask` = the lanes that take part (call warp-uniformly)
+#define RTX_COUNT_STEP( k, mask ) do { const unsigned m_ = ( mask ) ; if ( ( threadIdx.x&31u ) == 0u ) { atomicAdd( &rtx::g_dev_steps[( k )&7], 1ull ) ; atomicAdd( &rtx::g_dev_lanes[( k )&7], ( unsigned long long ) __popc( m_ ) ) ; } } while ( 0 )   // (the mask is a warp vote: every lane evaluates it)
+// a ray of a path's bounce b (0 = primary) has been traced
+#define RTX_COUNT_LIVE( b ) ( ( void ) atomicAdd( &rtx::g_dev_live[( b )<63u ? ( b ) : 63u], 1ull ) )
+#else
+#define RTX_COUNT_STEP( k, mask ) ( ( void ) 0 )
+#define RTX_COUNT_LIVE( b ) ( ( void ) 0 )
 #endif
 
 namespace rtx {

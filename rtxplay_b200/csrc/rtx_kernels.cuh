@@ -224,6 +224,7 @@ __global__ void RTX_RENDER_BOUNDS k_render( const __grid_constant__ FrameArgs a,
 				// vote) while enough lanes still have one
 				int jn = j ;
 				while ( true ) {
+					RTX_COUNT_STEP( K_NODE, __ballot_sync( 0xffffffffu, jn>=0 ) ) ;
 					if ( jn>=0 ) {
 						const int kn = step_node( p, jn*32+int( lane ), a.S ) ;
 #pragma unroll
@@ -239,12 +240,15 @@ __global__ void RTX_RENDER_BOUNDS k_render( const __grid_constant__ FrameArgs a,
 				break ;
 			}
 			case K_LEAF:
+				RTX_COUNT_STEP( K_LEAF, __ballot_sync( 0xffffffffu, j>=0 ) ) ;
 				if ( j>=0 ) nk = step_leaf( p, slot, a.S ) ;
 				break ;
 			case K_THING:
+				RTX_COUNT_STEP( K_THING, __ballot_sync( 0xffffffffu, j>=0 ) ) ;
 				if ( j>=0 ) nk = step_thing( p, slot, a.S ) ;
 				break ;
 			case K_SHADE:
+				RTX_COUNT_STEP( K_SHADE, __ballot_sync( 0xffffffffu, j>=0 ) ) ;
 				if ( j>=0 ) {
 					f3 c, gn, ga ; bool g ;
 					uint32_t segments ;
@@ -271,6 +275,7 @@ __global__ void RTX_RENDER_BOUNDS k_render( const __grid_constant__ FrameArgs a,
 				break ;
 			default: {   // K_REGEN: hand the next paths of the warp's unit(s) to the lanes that ask
 				uint32_t want = __ballot_sync( 0xffffffffu, j>=0 ) ;
+				RTX_COUNT_STEP( K_REGEN, want ) ;
 				while ( want ) {
 					if ( unit_left == 0 && ! exhausted ) {
 						uint32_t u = 0 ;
@@ -429,6 +434,50 @@ __global__ void __launch_bounds__( 256 ) k_resolve( const uint64_t* accum, uint3
 		raw[3*size_t( p )+c] = 0.f>v ? 0.f : v>1.f ? 1.f : v ;
 	}
 	rpp[p] = uint32_t( hi.y ) ;
+}
+
+// Multi-GPU frame (rtx_init_multi): the devices' fixed-point accumulation buffers summed by ONE
+// kernel on the root that reads the replicas' buffers through peer memory (NVLink / NVSwitch),
+// writes the total back as the root's buffer and, when asked, resolves it in the same pass --
+// the reduce of SURVEY.md 8(e) fused with the mean + clamp that has to follow it (optx/camera_i.cu:105).
+// Integer sums: the result does not depend on the number of devices.
+#define RTX_MAX_DEVICES 8
+struct PeerBufs { const uint64_t* accum[RTX_MAX_DEVICES] ; const long long* guide[RTX_MAX_DEVICES] ; int n ; } ;
+__global__ void __launch_bounds__( 256 ) k_reduce_resolve( const PeerBufs pb, uint64_t* accum0, uint32_t npix, uint64_t total_spp, int resolve, float* raw, uint32_t* rpp,
+		long long* guide0, float* normals, float* albedos ) {
+	const uint32_t p = blockIdx.x*blockDim.x+threadIdx.x ;
+	if ( p>=npix )
+		return ;
+	ulonglong2 lo = reinterpret_cast<const ulonglong2*>( pb.accum[0] )[2*size_t( p )] ;
+	ulonglong2 hi = reinterpret_cast<const ulonglong2*>( pb.accum[0] )[2*size_t( p )+1] ;
+	for ( int r = 1 ; r<pb.n ; r++ ) {
+		const ulonglong2 l2 = reinterpret_cast<const ulonglong2*>( pb.accum[r] )[2*size_t( p )] ;
+		const ulonglong2 h2 = reinterpret_cast<const ulonglong2*>( pb.accum[r] )[2*size_t( p )+1] ;
+		lo.x += l2.x ; lo.y += l2.y ; hi.x += h2.x ; hi.y += h2.y ;
+	}
+	reinterpret_cast<ulonglong2*>( accum0 )[2*size_t( p )] = lo ;
+	reinterpret_cast<ulonglong2*>( accum0 )[2*size_t( p )+1] = hi ;
+	const double n = double( total_spp ) ;
+	if ( resolve ) {
+		const uint64_t s[3] = { lo.x, lo.y, hi.x } ;
+		for ( int c = 0 ; c<3 ; c++ ) {
+			const float v = float( double( s[c] )*( 1./4294967296. )/n ) ;
+			raw[3*size_t( p )+c] = 0.f>v ? 0.f : v>1.f ? 1.f : v ;
+		}
+		rpp[p] = uint32_t( hi.y ) ;
+	}
+	if ( guide0 ) {
+		long long g[6] ;
+		for ( int c = 0 ; c<6 ; c++ ) g[c] = pb.guide[0][6*size_t( p )+c] ;
+		for ( int r = 1 ; r<pb.n ; r++ )
+			for ( int c = 0 ; c<6 ; c++ ) g[c] += pb.guide[r][6*size_t( p )+c] ;
+		for ( int c = 0 ; c<6 ; c++ ) guide0[6*size_t( p )+c] = g[c] ;
+		if ( resolve )
+			for ( int c = 0 ; c<3 ; c++ ) {
+				normals[3*size_t( p )+c] = float( double( g[c] )*( 1./1073741824. )/n ) ;
+				albedos[3*size_t( p )+c] = float( double( g[3+c] )*( 1./1073741824. )/n ) ;
+			}
+	}
 }
 
 // guide layers: mean of the fixed-point sums (optx/camera_i.cu:109-113)

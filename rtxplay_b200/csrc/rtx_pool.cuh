@@ -506,6 +506,7 @@ template <class P> RTX_HD int step_shade( P& p, int slot, const SceneDev& S, f3&
 	const uint32_t meta = uint32_t( p.i( F_META, slot ) )+512u ;   // bits 0-7 depth left, 8 guide taken, 9-15 segments of the path
 	const uint32_t depth_left = meta&255u ;
 	segments = meta>>9 ;
+	RTX_COUNT_LIVE( segments-1u ) ;
 	c = mk3( 0.f, 0.f, 0.f ) ;
 	if ( h.thing<0 ) {
 		c = thr*sky( dir ) ;

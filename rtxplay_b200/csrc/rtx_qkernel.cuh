@@ -77,6 +77,7 @@ __global__ void __launch_bounds__( 32, RTX_Q_MIN_CTAS ) k_render_q( const __grid
 		int slot = 0 ;
 		int nk = K_DONE ;
 		bool may_regen = false ;
+		RTX_COUNT_STEP( kind, take>=32u ? 0xffffffffu : ( 1u<<take )-1u ) ;
 		// take the first `take` slots of queue k (k = 1..4)
 #define RTX_QTAKE( k ) { \
 			const uint32_t sh = 8u*( k-1u ), hd = ( H>>sh )&127u ; \

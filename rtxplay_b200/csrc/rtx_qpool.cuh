@@ -356,6 +356,7 @@ template <class P> RTX_HD int qstep_shade( P& p, int slot, const SceneDev& S, f3
 	const uint32_t meta = bitsu( c1.w )+512u ;   // bits 0-7 depth left, 8 guide taken, 9-15 segments of the path
 	const uint32_t depth_left = meta&255u ;
 	segments = meta>>9 ;
+	RTX_COUNT_LIVE( segments-1u ) ;
 	c = mk3( 0.f, 0.f, 0.f ) ;
 	if ( h_thing<0 ) {
 		c = thr*sky( dir ) ;

@@ -30,6 +30,7 @@ Args::Args( const int argc, char* const* argv ) noexcept( false ) {
 		{ "apply-denoiser",    required_argument, 0,   'D' },
 		{ "analytic",          no_argument,       &analytic_, 1 },
 		{ "device",            required_argument, 0,   1000 },
+		{ "gpus",              required_argument, 0,   1001 },
 		{ 0, 0, 0, 0 }
 	} ;
 	optind = 1 ;
@@ -85,6 +86,7 @@ Args::Args( const int argc, char* const* argv ) noexcept( false ) {
 				break ;
 			}
 			case 1000: device_ = abs( atoi( optarg ) ) ; break ;
+			case 1001: gpus_ = abs( atoi( optarg ) ) ; break ;
 			case '?':
 				throw std::invalid_argument( "try 'rtwo --help' for more information." ) ;
 			default: // 0: a flag was stored by getopt_long
@@ -133,6 +135,8 @@ void Args::usage() {
 "Additional:\n"
 "      --analytic                          analytic spheres (the CPU path's geometry) instead of meshes\n"
 "      --device N                          CUDA device index\n"
+"      --gpus N                            render on N GPUs of this node (devices N0 .. N0+N-1, N0 = --device):\n"
+"                                          the samples of the frame are split, the sums reduced on the first\n"
 "\n" ;
 }
 

@@ -54,6 +54,8 @@ class Args {
 		// instead of the tessellated meshes; --device N selects the GPU
 		bool flag_analytic()              const { return analytic_>0 ; }
 		int  param_device( const int dEfault ) const { return 0>device_ ? dEfault : device_ ; }
+		// additive: --gpus N spreads a frame over N devices (rtx_init_multi)
+		int  param_gpus( const int dEfault ) const { return 1>gpus_ ? dEfault : gpus_ ; }
 
 		static void usage() ;
 
@@ -63,7 +65,7 @@ class Args {
 		Dns D_typ_ = Dns::NONE ;
 		int v_ = 0, h_ = 0, q_ = 0, t_ = 0, G_ = 0, S_ = 0 ;
 		Aov A_rpp_ = Aov::NONE ;
-		int analytic_ = 0, device_ = -1 ;
+		int analytic_ = 0, device_ = -1, gpus_ = -1 ;
 } ;
 
 #endif // ARGS_H

@@ -184,6 +184,16 @@ int main( int argc, char* argv[] ) {
 
 	rtx_ctx* context = nullptr ;
 	try {
+		const int gpus = args.param_gpus( 1 ) ;
+		if ( gpus>1 ) {
+			// additive: one context over several devices (the reference is single-context, optx/rtwo.cxx:126-127)
+			int present = 0 ;
+			CUDA_CHECK( cudaGetDeviceCount( &present ) ) ;
+			std::vector<int> ids ;
+			for ( int k = 0 ; k<gpus ; k++ ) ids.push_back( ( args.param_device( 0 )+k )%( present>0 ? present : 1 ) ) ;
+			if ( rtx_init_multi( gpus, ids.data(), &context ) != 0 )
+				throw std::runtime_error( std::string( "RTX error: rtx_init_multi : " )+rtx_last_error( nullptr )+"\n" ) ;
+		} else
 		if ( rtx_init( args.param_device( 0 ), &context ) != 0 )
 			throw std::runtime_error( std::string( "RTX error: rtx_init : " )+rtx_last_error( nullptr )+"\n" ) ;
 

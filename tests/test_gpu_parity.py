@@ -407,6 +407,10 @@ def test_counted_traversal_work_equals_host_harness(spheres):
     s = hostemu.stats()
     assert c["segments"] == int(e["rpp"].sum())
     assert c["rays"] == c["segments"] == s["rays"]
+    # rtx_frame_stats (include/rtx.h): paths alive per bounce and lanes per step kind from the kernel's own counters
+    assert c["live_paths"][0] == w * h * spp and sum(c["live_paths"]) == c["segments"]
+    assert all(a >= b for a, b in zip(c["live_paths"], c["live_paths"][1:]))
+    assert all(0. < c["lanes_per_step"][k] <= 32. for k in ("node", "leaf", "thing", "shade", "regen"))
     # the mesh hierarchies are the same trees; the top-level boxes are not bit-identical (the device
     # rounds a thing's eight transformed corners outward, the harness pads them), which moves a few
     # visits in ten thousand: measured 537405 against 537777 node steps
@@ -414,3 +418,78 @@ def test_counted_traversal_work_equals_host_harness(spheres):
     for k_dev, k_host, tol in (("nodes", "nodes", .005), ("leaves", "leaves", .005), ("tris", "tris", .005), ("things", "things", .005),
                                ("culled_or_sphere_tests", "spheres", .05)):
         assert abs(c[k_dev] - s[k_host]) <= tol * s[k_host], (k_dev, c[k_dev], s[k_host])
+
+
+@pytest.mark.parametrize("mode,ndiv,devices", [("analytic", None, [0, 0]), ("mesh", 2, [0, 0, 0])])
+def test_multi_device_context_equals_single_device(spheres, mode, ndiv, devices):
+    """rtx_init_multi (include/rtx.h): one context over several device replicas -- the scene calls fan
+    out, a frame's samples are split (device r traces samples r, r+n, ...), one kernel on the root sums
+    the replicas' fixed-point buffers through peer memory and resolves.  The frame equals the
+    one-device frame bit for bit (sums, segments, rawRGB, guide layers), for a sample count the
+    devices do not divide, for fewer samples than devices, and for accumulated frames.  On a
+    single-GPU box the replicas share device 0 (the driver's SCALE run covers real peers)."""
+    one, tab, meshes = _ctx(spheres, mode, ndiv)
+    many = api.Context(devices=devices)
+    assert many.device_count() == len(devices)
+    scenes.load(many, spheres, mode, ndiv)
+    w, h = 72, 48
+    cam = api.camera(aspratio=w / h)
+    for ctx in (one, many):
+        ctx.resize(w, h)
+    for spp in (5, 1):
+        for ctx in (one, many):
+            ctx.render(ctx.params(cam, spp, guides=1))
+        assert np.array_equal(many.read(api.BUF_ACCUM), one.read(api.BUF_ACCUM))
+        assert np.array_equal(many.read(api.BUF_RAWRGB), one.read(api.BUF_RAWRGB))
+        assert np.array_equal(many.read(api.BUF_RPP), one.read(api.BUF_RPP))
+        assert np.array_equal(many.read(api.BUF_GUIDE_ACC), one.read(api.BUF_GUIDE_ACC))
+        assert np.array_equal(many.read(api.BUF_NORMALS), one.read(api.BUF_NORMALS))
+        assert many.stats()["segments"] == one.stats()["segments"]
+    ref = orc.render(orc.F32_PCG, tab, api.camera_table(cam), w, h, 1, 50, meshes=meshes)
+    assert np.array_equal(many.read(api.BUF_ACCUM)[..., :3], ref["fix"])
+    # progressive accumulation: 3 + 4 samples in two calls == 7 in one
+    one.render(one.params(cam, 7))
+    many.render_accumulate(many.params(cam, 3))
+    many.render_accumulate(many.params(cam, 4, sample0=3, accumulate=1))
+    many.resolve(7)
+    assert np.array_equal(many.read(api.BUF_ACCUM), one.read(api.BUF_ACCUM))
+    assert np.array_equal(many.read(api.BUF_RAWRGB), one.read(api.BUF_RAWRGB))
+    # a transform edit + refit reaches every replica
+    big = len(spheres) - 2
+    xf = one.get_xf(big)
+    xf[7] += 1.
+    for ctx in (one, many):
+        ctx.set_xf(big, xf)
+        ctx.update()
+        ctx.render(ctx.params(cam, 2))
+    assert np.array_equal(many.read(api.BUF_ACCUM), one.read(api.BUF_ACCUM))
+    one.close()
+    many.close()
+
+
+def test_rtwo_scene_files_gpus_and_ppm_bytes(tmp_path):
+    """rtwo (optx/rtwo.cxx:138-145): meshes from sphere_{3,6,8,9}.scn when present, else what the
+    `sphere` tool would have written -- the same frame either way; --gpus 2 -- the same frame; and the
+    PPM bytes are the explicit sRGB transfer (rtx_kernels.cuh srgb_pow) of the frame's rawRGB."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    host = os.path.join(root, "rtxplay_b200", "host")
+    subprocess.check_call(["make", "-C", host], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    exe = os.path.join(host, "rtwo")
+    with_files, without = tmp_path / "with", tmp_path / "without"
+    with_files.mkdir()
+    without.mkdir()
+    subprocess.check_call(["make", "-C", host, "scenes", "SCENE_DIR=%s" % with_files], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    assert sorted(os.listdir(with_files)) == ["sphere_3.scn", "sphere_6.scn", "sphere_8.scn", "sphere_9.scn"]
+    argv = [exe, "-g", "96x64", "-s", "2", "-d", "50"]
+    raw_file = str(tmp_path / "raw.f32")
+    a = subprocess.run(argv, cwd=with_files, stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True, env=dict(os.environ, RTWO_DUMP_RAW=raw_file))
+    b = subprocess.run(argv, cwd=without, stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True)
+    c = subprocess.run(argv + ["--gpus", "2"], cwd=without, stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True)
+    assert a.stdout == b.stdout == c.stdout
+    tok = a.stdout.split()
+    assert tok[:4] == [b"P3", b"96", b"64", b"255"]
+    rgb = np.array(tok[4:4 + 3 * 96 * 64], dtype=np.uint8).reshape(64, 96, 3)
+    raw = np.fromfile(raw_file, dtype=np.float32).reshape(64, 96, 3)
+    assert np.array_equal(rgb[::-1], orc.srgb8(raw, srgb=True)[..., :3])      # rows are written bottom-up
