@@ -61,6 +61,7 @@ def parse():
     ap.add_argument("--count-spp", type=int, default=4, help="samples per pixel of the counted-work frame")
     ap.add_argument("--count-worker", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--cpu-worker", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (long configurations: the e2e fields then repeat the device-timed ones and say so)")
     ap.add_argument("--no-rtow", action="store_true", help="skip the run of the unmodified reference binary oracle/_ref/rtow (~80 s on one core)")
     return ap.parse_args()
 
@@ -161,8 +162,8 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    rtow = None if a.no_rtow else RtowRun()
     val, cores, desc, ms = cpu_leg(a, a.cpu_spp, steps=max(a.steps, 1), warmup=min(a.warmup, 1))
+    rtow = None if a.no_rtow else RtowRun()                   # after the port's steps: alone on the box
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -174,6 +175,7 @@ def run_reference(a):
     }
     if rtow is not None:
         line["cpu_baseline"]["reference_binary"] = rtow.result()
+        line["cpu_baseline"]["reference_binary"]["note"] = "ran alone, after the timed steps of the port"
     print(json.dumps(line), flush=True)
 
 
@@ -350,7 +352,7 @@ def run_b200(a):
     if world > 1:
         dist.broadcast(seg_t, src=0)
     segments = int(seg_t.item())
-    e2e_dev, e2e_wall, _ = timed(a.steps, True)
+    e2e_dev, e2e_wall, _ = timed(a.steps, True) if not a.no_e2e else (ms_dev, ms_wall, 0.)
     if sampler:
         sampler.stop_flag = True
         sampler.join(timeout=2)
@@ -371,15 +373,48 @@ def run_b200(a):
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         achieved = segs_launch * bytes_seg / (k_ms * 1e-3) / 1e9
-        # DRAM bytes of the kernel from the committed ncu capture of this same configuration
-        traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "r01_k_render_traffic.json")
-        if os.path.exists(tpath) and world == 1 and a.scene == "book1" and a.mode == "mesh" and a.ndiv is None and (a.width, a.height, a.spp) == (1200, 800, 500):
-            t = json.load(open(tpath))
-            traffic, traffic_src = t["dram_bytes_read"] + t["dram_bytes_write"], "profiles/r01_k_render_traffic.json (" + t["source"] + ")"
+        # committed ncu captures of this same configuration: DRAM bytes of one frame (proof that the working set is
+        # cache resident) and the kernel's executed warp instructions / lanes per instruction per segment
+        traffic, traffic_src, issue = None, None, None
+        std_cfg = world == 1 and a.scene == "book1" and a.mode == "mesh" and a.ndiv is None and (a.width, a.height, a.spp) == (1200, 800, 500)
+        for rnd in ("r02", "r01"):
+            tpath = os.path.join(ROOT, "profiles", rnd + "_k_render_traffic.json")
+            if traffic is None and os.path.exists(tpath) and std_cfg:
+                t = json.load(open(tpath))
+                traffic, traffic_src = t["dram_bytes_read"] + t["dram_bytes_write"], "profiles/%s_k_render_traffic.json (%s)" % (rnd, t["source"])
+            ipath = os.path.join(ROOT, "profiles", rnd + "_k_render_issue.json")
+            if issue is None and os.path.exists(ipath) and a.scene == "book1" and a.mode == "mesh" and a.ndiv is None:
+                issue = json.load(open(ipath))
+                issue["file"] = "profiles/%s_k_render_issue.json" % rnd
         clocks = sampler.summary() if sampler else {}
         sm_mhz = clocks.get("sm_mhz") or 1965
         fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+        # The bound the kernel has (profiles/): instruction issue x SIMD efficiency.  achieved = warp
+        # instructions issued per second = (warp instructions per segment of the committed ncu capture) x segments of
+        # the launch / its CUDA-event duration measured here; peak = 4 schedulers x 148 SMs x the SM clock under load.
+        issue_peak = 148 * 4 * sm_mhz * 1e6 / 1e9
+        if issue is not None:
+            issue_ach = issue["warp_instructions_per_segment"] * segs_launch / (k_ms * 1e-3) / 1e9
+            roof = {"bound": "issue", "kernel": issue.get("kernel", "k_render"), "achieved": issue_ach, "peak": issue_peak, "unit": "Gwarp-inst/s",
+                    "frac": issue_ach / issue_peak, "peak_source": "4 warp schedulers x 148 SMs x %d MHz (median SM clock sampled during the timed region)" % sm_mhz,
+                    "simd": {"lanes_per_instruction": issue["lanes_per_instruction"], "frac": issue["lanes_per_instruction"] / 32.,
+                             "lane_instructions_per_segment": issue["warp_instructions_per_segment"] * issue["lanes_per_instruction"]},
+                    "useful_frac": issue_ach / issue_peak * issue["lanes_per_instruction"] / 32.,
+                    "ncu": {k: issue.get(k) for k in ("issue_active_pct", "l1_data_pipe_pct", "l1_hit_pct", "l2_hit_pct", "registers", "warps_active_pct", "file", "command")},
+                    "note": "issue slots used x lanes per instruction: the kernel is bound by instruction issue and SIMD efficiency with the L1 data pipe as co-limiter (DESIGN.md 4); "
+                            "`traffic` = DRAM bytes of one frame from the committed ncu pass, against %.1f TB of algorithmic node + primitive bytes -- the working set is L1/L2 resident, "
+                            "so HBM is not the bound (the contract's hbm figure is kept under `hbm_model`)" % (segs_launch * bytes_seg / 1e12)}
+        else:
+            roof = {"bound": "issue", "kernel": "k_render", "achieved": None, "peak": issue_peak, "unit": "Gwarp-inst/s", "frac": None,
+                    "note": "no committed ncu capture for this configuration (profiles/rNN_k_render_issue.json): issue-slot figures unavailable; see hbm_model / l2 / fp32"}
+        roof.update({"traffic": traffic, "traffic_source": traffic_src, "kernel_ms": k_ms, "bytes_per_segment": bytes_seg,
+                     "hbm_model": {"achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                                   "what": "algorithmic bytes per segment of SURVEY.md 8(d), 64*ceil(log2 N) + 48 + 128, x segments / kernel time: a cache-bandwidth figure quoted against the HBM peak"},
+                     "l2": {"achieved": achieved, "peak": l2_peak, "unit": "GB/s", "frac": achieved / l2_peak if l2_peak else None,
+                            "peak_source": "measured in this run: rtx_probe_read, 32 MiB buffer read 1000x by all SMs with ld.global.cg.v4"},
+                     "fp32": {"flop_per_segment": flop_seg, "achieved_tflops": segs_launch * flop_seg / (k_ms * 1e-3) / 1e12,
+                              "peak_tflops": fp32_peak, "frac": segs_launch * flop_seg / (k_ms * 1e-3) / 1e12 / fp32_peak}})
+        fs = ctx.frame_stats()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -389,17 +424,12 @@ def run_b200(a):
                        "things": st["n_things"], "triangles_instanced": st["n_triangles_instanced"], "triangles_stored": st["n_triangles"],
                        "parallelism": "spp split over %d rank(s) + NCCL reduce of the u64 accumulation buffer" % world if world > 1 else "1 GPU",
                        "l2": "256 MiB device write between steps (inside the timed region)",
+                       "kernel": "k_render_q (compacting ray pool)" if fs["kernel"] else "k_render (one ray per lane)",
+                       "stage_ms_last_frame": {k: fs[k] for k in ("ms_frame", "ms_trace", "ms_reduce_resolve", "ms_postproc")},
                        "ms_per_frame": ms_step, "ms_per_frame_e2e": e2e_ms, "wall_ms_per_step": ms_wall / a.steps},
-            "roofline": {"bound": "hbm", "kernel": "k_render", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                         "bytes_per_segment": bytes_seg, "kernel_ms": k_ms,
-                         "note": "algorithmic node+primitive bytes of SURVEY.md 8(d); the working set is L1/L2 resident (`traffic` = DRAM bytes of one launch from the ncu capture, against %.1f TB of algorithmic bytes), so this is a cache-bandwidth figure quoted against the HBM peak; the kernel is bound by instruction issue and SIMD efficiency (DESIGN.md 4)" % (segs_launch * bytes_seg / 1e12),
-                         "l2": {"achieved": achieved, "peak": l2_peak, "unit": "GB/s", "frac": achieved / l2_peak if l2_peak else None,
-                                "peak_source": "measured in this run: rtx_probe_read, 32 MiB buffer read 1000x by all SMs with ld.global.cg.v4"},
-                         "fp32": {"flop_per_segment": flop_seg, "achieved_tflops": segs_launch * flop_seg / (k_ms * 1e-3) / 1e12,
-                                  "peak_tflops": fp32_peak, "frac": segs_launch * flop_seg / (k_ms * 1e-3) / 1e12 / fp32_peak}},
+            "roofline": roof,
             "e2e": {"value": segments / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": ctypes.sizeof(ctx.params(cam, 1)),
-                    "d2h_bytes_per_step": int(image_host.numel()), "ms_per_frame": e2e_ms},
+                    "d2h_bytes_per_step": int(image_host.numel()), "ms_per_frame": e2e_ms, **({"skipped": "--no-e2e: these repeat the device-timed frame"} if a.no_e2e else {})},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }

@@ -171,6 +171,15 @@ struct q4 { float x, y, z, w ; } ;   // 16-byte record, bit-compatible with floa
 #define RTX_WIDTH      4            // children per node: 4, or 8 (experimental: two such 128-byte blocks per node, children 0-3 and 4-7)
 #endif
 #define RTX_NODE_RECS  ( 2*RTX_WIDTH )
+// Child boxes of a 4-wide node are stored in centre / half-extent form (r0..r2 = centre x, y, z of the
+// four children, r3..r5 = half extents): the slab test then needs no min / max per plane pair --
+// t_near = (c.d' - o.d') - h|d'|, t_far = ... + h|d'| are three multiply-adds per axis -- 18 packed FMAs
+// instead of 12 packed FMAs + 24 min/max per node step (the FMA pipe has room, the ALU pipe does not).
+// [c-h, c+h] contains the padded [lo, hi] (box_ch rounds h up); an unused slot is c = +inf, h = 0.
+// (The experimental 8-wide layout keeps lo / hi.)
+#ifndef RTX_NODE_CH
+#define RTX_NODE_CH    ( RTX_WIDTH == 4 )
+#endif
 #define RTX_TRI_RECS   4            // a triangle: (a, prim id) (e1, b.x) (e2, b.y) (b.z, c) = 64 bytes, two 256-bit loads
 #ifndef RTX_LEAF_MAX
 #define RTX_LEAF_MAX   3            // triangles per mesh leaf, at most 8 (top level: 1 thing per leaf); measured 2/3/4/6/8: 708/684/698/690/697 ms
@@ -401,6 +410,17 @@ RTX_HD bool better( float t, int32_t thing, int32_t prim, const HitRec& best ) {
 // relative slack): may visit too much, never too little.  This is the one place where
 // FMA and an approximate reciprocal are used on purpose -- it never decides a result.
 #define RTX_SLACK 1.0000038f
+// one axis of a child box for the node record: (lo, hi) -> what the record stores
+RTX_HD void box_ch( float lo, float hi, float& a, float& b ) {
+#if RTX_NODE_CH
+	if ( lo == INFINITY ) { a = INFINITY ; b = 0.f ; return ; }   // unused slot: entered by no ray
+	const float c = .5f*lo+.5f*hi ;
+	a = c ;
+	b = fmaxf( hi-c, c-lo )*1.000001f+1e-37f ;                      // rounded up: [c-b, c+b] contains [lo, hi]
+#else
+	a = lo ; b = hi ;
+#endif
+}
 RTX_HD float safe_rcp( float d ) {
 	// 1/d clamped to +-1e30: a zero component gives a huge finite slope instead of inf, so
 	// that o*idir and the slab products stay finite (no inf-inf, no 0*inf)
@@ -416,12 +436,24 @@ RTX_HD float safe_rcp( float d ) {
 }
 // entry distance of the ray into box (lo,hi), or +inf when it misses [tmin, tbest]
 RTX_HD float slab( float lox, float loy, float loz, float hix, float hiy, float hiz, const f3& idir, const f3& ood, float tmin, float tbest_s ) {
+#if RTX_NODE_CH
+	// (lox.. are the centre, hix.. the half extents)
+	const float tx = fmaf( lox, idir.x, -ood.x ), ty = fmaf( loy, idir.y, -ood.y ), tz = fmaf( loz, idir.z, -ood.z ) ;
+	const float ax = fabsf( idir.x ), ay = fabsf( idir.y ), az = fabsf( idir.z ) ;
+	const float x0 = fmaf( hix, -ax, tx ), x1 = fmaf( hix, ax, tx ) ;
+	const float y0 = fmaf( hiy, -ay, ty ), y1 = fmaf( hiy, ay, ty ) ;
+	const float z0 = fmaf( hiz, -az, tz ), z1 = fmaf( hiz, az, tz ) ;
+	const float tn = fmaxf( fmaxf( x0, y0 ), fmaxf( z0, tmin ) ) ;
+	const float tf = fminf( fminf( x1, y1 ), fminf( z1, tbest_s ) ) ;
+	return tn<=tf*RTX_SLACK ? tn : INFINITY ;
+#else
 	const float x0 = fmaf( lox, idir.x, -ood.x ), x1 = fmaf( hix, idir.x, -ood.x ) ;
 	const float y0 = fmaf( loy, idir.y, -ood.y ), y1 = fmaf( hiy, idir.y, -ood.y ) ;
 	const float z0 = fmaf( loz, idir.z, -ood.z ), z1 = fmaf( hiz, idir.z, -ood.z ) ;
 	const float tn = fmaxf( fmaxf( fminf( x0, x1 ), fminf( y0, y1 ) ), fmaxf( fminf( z0, z1 ), tmin ) ) ;
 	const float tf = fminf( fminf( fmaxf( x0, x1 ), fmaxf( y0, y1 ) ), fminf( fmaxf( z0, z1 ), tbest_s ) ) ;
 	return tn<=tf*RTX_SLACK ? tn : INFINITY ;
+#endif
 }
 
 #ifndef RTX_W8_ORDER
@@ -475,9 +507,38 @@ __device__ __forceinline__ void fma2( float a0, float a1, float s, float c, floa
 	const float2 rv = *reinterpret_cast<float2*>( &r ) ;
 	r0 = rv.x ; r1 = rv.y ;
 }
+// (a0,a1)*s + (c0,c1)
+__device__ __forceinline__ void fma2p( float a0, float a1, float s, float c0, float c1, float& r0, float& r1 ) {
+	float2 av = make_float2( a0, a1 ), sv = make_float2( s, s ), cv = make_float2( c0, c1 ) ;
+	unsigned long long r ;
+	asm( "fma.rn.f32x2 %0, %1, %2, %3;" : "=l"( r ) : "l"( *reinterpret_cast<unsigned long long*>( &av ) ), "l"( *reinterpret_cast<unsigned long long*>( &sv ) ), "l"( *reinterpret_cast<unsigned long long*>( &cv ) ) ) ;
+	const float2 rv = *reinterpret_cast<float2*>( &r ) ;
+	r0 = rv.x ; r1 = rv.y ;
+}
 __device__ __forceinline__ void slab4( const q4& lx, const q4& ly, const q4& lz, const q4& hx, const q4& hy, const q4& hz, const f3& idir, const f3& ood, float tmin, float tbest_s,
 		float& t0, float& t1, float& t2, float& t3 ) {
 	float x0[4], x1[4], y0[4], y1[4], z0[4], z1[4] ;
+#if RTX_NODE_CH
+	// centre / half-extent records: per axis t = c d' - o d', near = t - h|d'|, far = t + h|d'|
+	float tx[4], ty[4], tz[4] ;
+	fma2( lx.x, lx.y, idir.x, ood.x, tx[0], tx[1] ) ; fma2( lx.z, lx.w, idir.x, ood.x, tx[2], tx[3] ) ;
+	fma2( ly.x, ly.y, idir.y, ood.y, ty[0], ty[1] ) ; fma2( ly.z, ly.w, idir.y, ood.y, ty[2], ty[3] ) ;
+	fma2( lz.x, lz.y, idir.z, ood.z, tz[0], tz[1] ) ; fma2( lz.z, lz.w, idir.z, ood.z, tz[2], tz[3] ) ;
+	const float ax = fabsf( idir.x ), ay = fabsf( idir.y ), az = fabsf( idir.z ) ;
+	fma2p( hx.x, hx.y, -ax, tx[0], tx[1], x0[0], x0[1] ) ; fma2p( hx.z, hx.w, -ax, tx[2], tx[3], x0[2], x0[3] ) ;
+	fma2p( hx.x, hx.y,  ax, tx[0], tx[1], x1[0], x1[1] ) ; fma2p( hx.z, hx.w,  ax, tx[2], tx[3], x1[2], x1[3] ) ;
+	fma2p( hy.x, hy.y, -ay, ty[0], ty[1], y0[0], y0[1] ) ; fma2p( hy.z, hy.w, -ay, ty[2], ty[3], y0[2], y0[3] ) ;
+	fma2p( hy.x, hy.y,  ay, ty[0], ty[1], y1[0], y1[1] ) ; fma2p( hy.z, hy.w,  ay, ty[2], ty[3], y1[2], y1[3] ) ;
+	fma2p( hz.x, hz.y, -az, tz[0], tz[1], z0[0], z0[1] ) ; fma2p( hz.z, hz.w, -az, tz[2], tz[3], z0[2], z0[3] ) ;
+	fma2p( hz.x, hz.y,  az, tz[0], tz[1], z1[0], z1[1] ) ; fma2p( hz.z, hz.w,  az, tz[2], tz[3], z1[2], z1[3] ) ;
+	float t[4] ;
+#pragma unroll
+	for ( int k = 0 ; k<4 ; k++ ) {
+		const float tn = fmaxf( fmaxf( x0[k], y0[k] ), fmaxf( z0[k], tmin ) ) ;
+		const float tf = fminf( fminf( x1[k], y1[k] ), fminf( z1[k], tbest_s ) ) ;
+		t[k] = tn<=tf*RTX_SLACK ? tn : INFINITY ;
+	}
+#else
 	fma2( lx.x, lx.y, idir.x, ood.x, x0[0], x0[1] ) ; fma2( lx.z, lx.w, idir.x, ood.x, x0[2], x0[3] ) ;
 	fma2( hx.x, hx.y, idir.x, ood.x, x1[0], x1[1] ) ; fma2( hx.z, hx.w, idir.x, ood.x, x1[2], x1[3] ) ;
 	fma2( ly.x, ly.y, idir.y, ood.y, y0[0], y0[1] ) ; fma2( ly.z, ly.w, idir.y, ood.y, y0[2], y0[3] ) ;
@@ -491,6 +552,7 @@ __device__ __forceinline__ void slab4( const q4& lx, const q4& ly, const q4& lz,
 		const float tf = fminf( fminf( fmaxf( x0[k], x1[k] ), fmaxf( y0[k], y1[k] ) ), fminf( fmaxf( z0[k], z1[k] ), tbest_s ) ) ;
 		t[k] = tn<=tf*RTX_SLACK ? tn : INFINITY ;
 	}
+#endif
 	t0 = t[0] ; t1 = t[1] ; t2 = t[2] ; t3 = t[3] ;
 }
 #endif

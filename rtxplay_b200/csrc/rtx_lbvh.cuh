@@ -322,6 +322,7 @@ __global__ void __launch_bounds__( 128 ) k_wide_level( const int2* frontier, uin
 	for ( int h = 0 ; h<RTX_WIDTH/4 ; h++ ) {   // one 128-byte block per four children
 		q4* o = nodes+size_t( item.y )*RTX_NODE_RECS+8*h ;
 		for ( int a = 0 ; a<3 ; a++ ) {
+			for ( int k = 4*h ; k<4*h+4 ; k++ ) box_ch( lo[a][k], hi[a][k], lo[a][k], hi[a][k] ) ;   // (centre / half extent for 4-wide nodes)
 			o[a]   = { lo[a][4*h], lo[a][4*h+1], lo[a][4*h+2], lo[a][4*h+3] } ;
 			o[3+a] = { hi[a][4*h], hi[a][4*h+1], hi[a][4*h+2], hi[a][4*h+3] } ;
 		}

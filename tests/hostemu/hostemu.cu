@@ -227,6 +227,7 @@ void build_tree( const std::vector<q4>& plo, const std::vector<q4>& phi, Tree& T
 			for ( int hh = 0 ; hh<RTX_WIDTH/4 ; hh++ ) {
 				q4* o = T.nodes.data()+size_t( item.y )*RTX_NODE_RECS+8*hh ;
 				for ( int a = 0 ; a<3 ; a++ ) {
+					for ( int k = 4*hh ; k<4*hh+4 ; k++ ) box_ch( lo[a][k], hi[a][k], lo[a][k], hi[a][k] ) ;
 					o[a]   = { lo[a][4*hh], lo[a][4*hh+1], lo[a][4*hh+2], lo[a][4*hh+3] } ;
 					o[3+a] = { hi[a][4*hh], hi[a][4*hh+1], hi[a][4*hh+2], hi[a][4*hh+3] } ;
 				}
