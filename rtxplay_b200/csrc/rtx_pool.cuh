@@ -353,7 +353,13 @@ template <class P> RTX_HD int step_node( P& p, int slot, const SceneDev& S ) {
 	// (unused child slots hold the box lo = hi = +inf, which no ray enters: no test needed)
 	// nearest child next, the others pushed far to near (a cheaper "nearest only" ordering was
 	// measured: 902 ms instead of 814 ms per frame -- the order of the pushed children matters)
+#if ! defined( RTX_SORT_MINMAX )
 #define RTX_CSWAP( ta, ca, tb, cb ) if ( tb<ta ) { const float tt = ta ; ta = tb ; tb = tt ; const int32_t cc = ca ; ca = cb ; cb = cc ; }
+#else
+	// (measured alternative: compare-exchange as min / max on the distances and two selects on the references --
+	// 599.9 against 594.4 ms per frame for the predicated swaps)
+#define RTX_CSWAP( ta, ca, tb, cb ) { const bool sw_ = tb<ta ; const float lo_ = fminf( ta, tb ), hi_ = fmaxf( ta, tb ) ; const int32_t cl_ = sw_ ? cb : ca, ch_ = sw_ ? ca : cb ; ta = lo_ ; tb = hi_ ; ca = cl_ ; cb = ch_ ; }
+#endif
 	RTX_CSWAP( t0, c0, t1, c1 ) RTX_CSWAP( t2, c2, t3, c3 ) RTX_CSWAP( t0, c0, t2, c2 ) RTX_CSWAP( t1, c1, t3, c3 ) RTX_CSWAP( t1, c1, t2, c2 )
 #undef RTX_CSWAP
 	if ( t0 == INFINITY )

@@ -218,7 +218,13 @@ template <class P> RTX_HD int qstep_node( P& p, int slot, const SceneDev& S ) {
 	float t2 = slab( lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, idir, ood, tmin, tbest_s ) ;
 	float t3 = slab( lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, idir, ood, tmin, tbest_s ) ;
 #endif
+#if ! defined( RTX_SORT_MINMAX )
 #define RTX_CSWAP( ta, ca, tb, cb ) if ( tb<ta ) { const float tt = ta ; ta = tb ; tb = tt ; const int32_t cc = ca ; ca = cb ; cb = cc ; }
+#else
+	// (measured alternative: compare-exchange as min / max on the distances and two selects on the references --
+	// 599.9 against 594.4 ms per frame for the predicated swaps)
+#define RTX_CSWAP( ta, ca, tb, cb ) { const bool sw_ = tb<ta ; const float lo_ = fminf( ta, tb ), hi_ = fmaxf( ta, tb ) ; const int32_t cl_ = sw_ ? cb : ca, ch_ = sw_ ? ca : cb ; ta = lo_ ; tb = hi_ ; ca = cl_ ; cb = ch_ ; }
+#endif
 	RTX_CSWAP( t0, c0, t1, c1 ) RTX_CSWAP( t2, c2, t3, c3 ) RTX_CSWAP( t0, c0, t2, c2 ) RTX_CSWAP( t1, c1, t3, c3 ) RTX_CSWAP( t1, c1, t2, c2 )
 #undef RTX_CSWAP
 	if ( t0 == INFINITY )
