@@ -136,6 +136,7 @@ struct rtx_ctx {
 	std::vector<long long*> stage_guide ;
 	std::vector<char>       peer_ok ;         // per replica: the root reads its memory directly
 	int       kernel = RTX_DEFAULT_KERNEL ;   // which path-tracing kernel do_render launches
+	uint32_t  wide_grid = 0 ;        // resident CTAs of the cooperative k_wide_all (0: no cooperative launch on this device)
 	uint32_t  q_grid = 0 ;           // k_render_q: resident warps, their cold ray records and overflow stacks
 	q4*       d_qcold = nullptr ;
 	int32_t*  d_qovf = nullptr ;
@@ -211,25 +212,36 @@ void lbvh_refit( rtx_ctx* c, Lbvh& b, const q4* plo, const q4* phi, int leaf_max
 	const int2 root = make_int2( 0, 0 ) ;
 	uint32_t counters[2] = { 1u, 0u } ;   // wide node 0 is the root
 	CK( cudaMemcpyAsync( b.front0, &root, sizeof( int2 ), cudaMemcpyHostToDevice, c->stream ) ) ;
-	uint32_t n_front = 1 ;
-	int2* fin = b.front0 ; int2* fout = b.front1 ;
-	while ( n_front ) {
-		counters[1] = 0 ;
-		CK( cudaMemcpyAsync( b.counters, counters, sizeof( counters ), cudaMemcpyHostToDevice, c->stream ) ) ;
-		k_wide_level<<<( n_front+127 )/128, 128, 0, c->stream>>>( fin, n_front, n, leaf_max, b.child, b.range, b.blo, b.bhi, b.nodes, fout, b.counters ) ;
+	CK( cudaMemcpyAsync( b.counters, counters, sizeof( counters ), cudaMemcpyHostToDevice, c->stream ) ) ;
+	if ( c->wide_grid ) {
+		// every level in one cooperative launch (frontier loop and level barriers on the device)
+		int n_arg = n, lm = leaf_max ;
+		void* args[] = { &b.front0, &b.front1, &n_arg, &lm, &b.child, &b.range, &b.blo, &b.bhi, &b.nodes, &b.counters } ;
+		CK( cudaLaunchCooperativeKernel( reinterpret_cast<const void*>( k_wide_all ), dim3( c->wide_grid ), dim3( 128 ), args, 0, c->stream ) ) ;
 		c->launches += 1 ;
-		CK( cudaGetLastError() ) ;
 		CK( cudaMemcpyAsync( counters, b.counters, sizeof( counters ), cudaMemcpyDeviceToHost, c->stream ) ) ;
-		CK( cudaStreamSynchronize( c->stream ) ) ;
-		n_front = counters[1] ;
-		std::swap( fin, fout ) ;
+	} else {
+		// (devices without cooperative launch: one launch per level, the host reads each frontier size)
+		uint32_t n_front = 1 ;
+		int2* fin = b.front0 ; int2* fout = b.front1 ;
+		while ( n_front ) {
+			k_wide_level<<<( n_front+127 )/128, 128, 0, c->stream>>>( fin, n_front, n, leaf_max, b.child, b.range, b.blo, b.bhi, b.nodes, fout, b.counters ) ;
+			c->launches += 1 ;
+			CK( cudaGetLastError() ) ;
+			CK( cudaMemcpyAsync( counters, b.counters, sizeof( counters ), cudaMemcpyDeviceToHost, c->stream ) ) ;
+			CK( cudaStreamSynchronize( c->stream ) ) ;
+			n_front = counters[1] ;
+			counters[1] = 0 ;
+			CK( cudaMemcpyAsync( b.counters, counters, sizeof( counters ), cudaMemcpyHostToDevice, c->stream ) ) ;
+			std::swap( fin, fout ) ;
+		}
 	}
-	b.n_nodes = counters[0] ;
 	CK( cudaEventRecord( c->stage_ev[5], c->stream ) ) ;
 	c->stage_full = false ;
 	CK( cudaMemcpyAsync( &b.root_lo, b.blo, sizeof( q4 ), cudaMemcpyDeviceToHost, c->stream ) ) ;
 	CK( cudaMemcpyAsync( &b.root_hi, b.bhi, sizeof( q4 ), cudaMemcpyDeviceToHost, c->stream ) ) ;
 	CK( cudaStreamSynchronize( c->stream ) ) ;
+	b.n_nodes = counters[0] ;
 }
 
 // Morton keys -> radix sort -> Karras hierarchy -> refit -> wide nodes
@@ -258,6 +270,8 @@ void lbvh_build( rtx_ctx* c, Lbvh& b, const q4* plo, const q4* phi, uint32_t n, 
 	uint64_t* keys0 = talloc<uint64_t>( c, n ) ; uint64_t* keys1 = talloc<uint64_t>( c, n ) ;
 	uint32_t* vals1 = talloc<uint32_t>( c, n ) ;
 	uint32_t* counts = talloc<uint32_t>( c, size_t( 256 )*nblocks ) ;
+	const uint32_t n_chunks = ( 256u*nblocks+RTX_SCAN_CHUNK-1u )/RTX_SCAN_CHUNK ;   // count-table scan: one block up to 16 K counters, else chunked
+	uint32_t* chunk_sums = talloc<uint32_t>( c, n_chunks ) ;
 
 	CK( cudaEventRecord( c->stage_ev[0], c->stream ) ) ;
 	k_bounds_init<<<1, 32, 0, c->stream>>>( bounds ) ;
@@ -270,7 +284,13 @@ void lbvh_build( rtx_ctx* c, Lbvh& b, const q4* plo, const q4* phi, uint32_t n, 
 	for ( int pass = 0 ; pass<8 ; pass++ ) {
 		const int shift = 8*pass ;
 		k_radix_hist<<<nblocks, 32*RTX_RS_WARPS, 0, c->stream>>>( kin, n, shift, counts, nblocks ) ;
-		k_radix_scan<<<1, 1024, 0, c->stream>>>( counts, 256u*nblocks ) ;
+		if ( n_chunks<=1u ) k_radix_scan<<<1, 1024, 0, c->stream>>>( counts, 256u*nblocks ) ;
+		else {
+			k_scan_chunks<<<n_chunks, 1024, 0, c->stream>>>( counts, 256u*nblocks, chunk_sums ) ;
+			k_radix_scan<<<1, 1024, 0, c->stream>>>( chunk_sums, n_chunks ) ;
+			k_scan_add<<<n_chunks, 1024, 0, c->stream>>>( counts, 256u*nblocks, chunk_sums ) ;
+			c->launches += 2 ;
+		}
 		k_radix_scatter<<<nblocks, 32*RTX_RS_WARPS, 0, c->stream>>>( kin, vin, n, shift, counts, nblocks, kout, vout ) ;
 		c->launches += 3 ;
 		std::swap( kin, kout ) ; std::swap( vin, vout ) ;
@@ -285,7 +305,7 @@ void lbvh_build( rtx_ctx* c, Lbvh& b, const q4* plo, const q4* phi, uint32_t n, 
 	lbvh_refit( c, b, plo, phi, leaf_max ) ;
 	c->stage_full = true ;
 
-	tfree( c, bounds, 6 ) ; tfree( c, keys0, n ) ; tfree( c, keys1, n ) ; tfree( c, vals1, n ) ; tfree( c, counts, size_t( 256 )*nblocks ) ;
+	tfree( c, bounds, 6 ) ; tfree( c, keys0, n ) ; tfree( c, keys1, n ) ; tfree( c, vals1, n ) ; tfree( c, counts, size_t( 256 )*nblocks ) ; tfree( c, chunk_sums, n_chunks ) ;
 	if ( ! keep_binary ) {
 		// a mesh is never refitted: drop the binary tree and trim the node array
 		lbvh_free_binary( c, b ) ;
@@ -656,7 +676,7 @@ int rtx_init( int device, rtx_ctx** out ) {
 			const void* kernels[] = { ( const void* ) k_render<false>, ( const void* ) k_render<true>, ( const void* ) k_primary_hits, ( const void* ) k_trace_rays, ( const void* ) k_pick,
 				( const void* ) k_resolve, ( const void* ) k_resolve_guides, ( const void* ) k_postproc, ( const void* ) k_sum_segments, ( const void* ) k_tri_bounds, ( const void* ) k_thing_bounds,
 				( const void* ) k_bounds_init, ( const void* ) k_bounds_reduce, ( const void* ) k_morton, ( const void* ) k_radix_hist, ( const void* ) k_radix_scan,
-				( const void* ) k_radix_scatter, ( const void* ) k_karras, ( const void* ) k_refit, ( const void* ) k_wide_level, ( const void* ) k_pack_tris } ;
+				( const void* ) k_radix_scatter, ( const void* ) k_karras, ( const void* ) k_refit, ( const void* ) k_wide_level, ( const void* ) k_wide_all, ( const void* ) k_scan_chunks, ( const void* ) k_scan_add, ( const void* ) k_pack_tris } ;
 			for ( const void* k : kernels ) CK( cudaFuncGetAttributes( &fa, k ) ) ;
 		}
 		// the render kernel is persistent: one warp per CTA, as many CTAs as fit
@@ -675,6 +695,12 @@ int rtx_init( int device, rtx_ctx** out ) {
 		if ( getenv( "RTX_VERBOSE" ) ) fprintf( stderr, "rtx_init: %d render warps per SM, carveout %d %%\n", per_sm, carve ) ;
 		c->render_grid = uint32_t( per_sm )*uint32_t( prop.multiProcessorCount ) ;
 		c->d_ovf = dalloc<int32_t>( c, size_t( c->render_grid )*RTX_POOL_R*RTX_POOL_OVF*2 ) ;
+		{	// the collapse into wide nodes runs all its levels in one cooperative launch
+			int coop = 0, wide_per_sm = 0 ;
+			CK( cudaDeviceGetAttribute( &coop, cudaDevAttrCooperativeLaunch, device ) ) ;
+			CK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &wide_per_sm, k_wide_all, 128, 0 ) ) ;
+			if ( coop && wide_per_sm>0 && ! getenv( "RTX_NO_COOP" ) ) c->wide_grid = uint32_t( std::min( wide_per_sm, 8 ) )*uint32_t( prop.multiProcessorCount ) ;
+		}
 		{	// the compacting-pool kernel: ray slots in dynamic shared memory
 			if ( const char* e = getenv( "RTX_KERNEL" ) ) c->kernel = ( e[0] == 'q' || e[0] == '1' ) ? 1 : 0 ;
 			int qcarve = RTX_Q_DEFAULT_CARVEOUT ;

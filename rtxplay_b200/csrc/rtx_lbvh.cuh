@@ -15,6 +15,9 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#if defined( __CUDACC__ )
+#include <cooperative_groups.h>
+#endif
 #include <stdint.h>
 
 #include "rtx_core.cuh"
@@ -207,6 +210,36 @@ __global__ void __launch_bounds__( 1024 ) k_radix_scan( uint32_t* counts, uint32
 	uint32_t run = threadIdx.x ? part[threadIdx.x-1] : 0u ;
 	for ( uint32_t i = a ; i<b ; i++ ) { const uint32_t c = counts[i] ; counts[i] = run ; run += c ; }
 }
+// the same over many blocks, for the count tables of big builds (256 counters per 2048 keys: 12.5 M
+// counters for 100 M keys): every block scans a chunk of RTX_SCAN_CHUNK counters in place and leaves
+// its total in sums[]; k_radix_scan then scans the (few hundred) totals; k_scan_add adds them back
+#define RTX_SCAN_CHUNK 16384u   // counters per block: 1024 threads x 16
+__global__ void __launch_bounds__( 1024 ) k_scan_chunks( uint32_t* counts, uint32_t m, uint32_t* sums ) {
+	__shared__ uint32_t part[1024] ;
+	const uint32_t base = blockIdx.x*RTX_SCAN_CHUNK+threadIdx.x*16u ;
+	uint32_t v[16], s = 0 ;
+	// (16 consecutive counters per thread: four 128-bit loads when the chunk is full)
+#pragma unroll
+	for ( int k = 0 ; k<16 ; k++ ) { v[k] = base+k<m ? counts[base+k] : 0u ; s += v[k] ; }
+	part[threadIdx.x] = s ;
+	__syncthreads() ;
+	for ( int o = 1 ; o<1024 ; o <<= 1 ) {
+		const uint32_t w = threadIdx.x>=o ? part[threadIdx.x-o] : 0u ;
+		__syncthreads() ;
+		part[threadIdx.x] += w ;
+		__syncthreads() ;
+	}
+	uint32_t run = threadIdx.x ? part[threadIdx.x-1] : 0u ;
+#pragma unroll
+	for ( int k = 0 ; k<16 ; k++ ) { if ( base+k<m ) counts[base+k] = run ; run += v[k] ; }
+	if ( threadIdx.x == 1023 ) sums[blockIdx.x] = part[1023] ;
+}
+__global__ void __launch_bounds__( 1024 ) k_scan_add( uint32_t* counts, uint32_t m, const uint32_t* sums ) {
+	const uint32_t add = sums[blockIdx.x] ;
+	const uint32_t base = blockIdx.x*RTX_SCAN_CHUNK+threadIdx.x*16u ;
+#pragma unroll
+	for ( int k = 0 ; k<16 ; k++ ) if ( base+k<m ) counts[base+k] += add ;
+}
 __global__ void __launch_bounds__( 32*RTX_RS_WARPS ) k_radix_scatter( const uint64_t* keys, const uint32_t* vals, uint32_t n, int shift, const uint32_t* offsets, uint32_t nblocks, uint64_t* keys_out, uint32_t* vals_out ) {
 	__shared__ uint32_t off[RTX_RS_WARPS][256] ;
 	const uint32_t lane = threadIdx.x&31u, warp = threadIdx.x>>5 ;
@@ -296,10 +329,7 @@ __global__ void __launch_bounds__( 256 ) k_refit( const q4* plo, const q4* phi, 
 // One level of the wide tree: work item = (binary inner node, wide node index).  Children
 // that stay inner get a fresh wide index and become work items of the next level.
 // counters[0] = wide nodes allocated so far, counters[1] = size of the next frontier.
-__global__ void __launch_bounds__( 128 ) k_wide_level( const int2* frontier, uint32_t n_front, int n, int leaf_max, const int2* child, const int2* range, const q4* blo, const q4* bhi, q4* nodes, int2* next, uint32_t* counters ) {
-	const uint32_t w = blockIdx.x*blockDim.x+threadIdx.x ;
-	if ( w>=n_front ) return ;
-	const int2 item = frontier[w] ;
+__device__ __forceinline__ void wide_item( const int2 item, int n, int leaf_max, const int2* child, const int2* range, const q4* blo, const q4* bhi, q4* nodes, int2* next, uint32_t* counters ) {
 	float lo[3][RTX_WIDTH], hi[3][RTX_WIDTH] ; int ref[RTX_WIDTH] ;
 	for ( int k = 0 ; k<RTX_WIDTH ; k++ ) { ref[k] = RTX_REF_EMPTY ; for ( int a = 0 ; a<3 ; a++ ) { lo[a][k] = INFINITY ; hi[a][k] = INFINITY ; } }   // an unused slot: a box no ray enters
 	if ( n == 1 ) {
@@ -328,6 +358,31 @@ __global__ void __launch_bounds__( 128 ) k_wide_level( const int2* frontier, uin
 		}
 		o[6] = { __int_as_float( ref[4*h] ), __int_as_float( ref[4*h+1] ), __int_as_float( ref[4*h+2] ), __int_as_float( ref[4*h+3] ) } ;
 		o[7] = { 0.f, 0.f, 0.f, 0.f } ;
+	}
+}
+__global__ void __launch_bounds__( 128 ) k_wide_level( const int2* frontier, uint32_t n_front, int n, int leaf_max, const int2* child, const int2* range, const q4* blo, const q4* bhi, q4* nodes, int2* next, uint32_t* counters ) {
+	const uint32_t w = blockIdx.x*blockDim.x+threadIdx.x ;
+	if ( w>=n_front ) return ;
+	wide_item( frontier[w], n, leaf_max, child, range, blo, bhi, nodes, next, counters ) ;
+}
+// All levels in one cooperative launch: the frontier loop runs on the device, levels separated by
+// grid barriers -- no host round trip per level (a 1 M-triangle mesh has ~12 levels, a flattened
+// 100 M-triangle one ~16).  counters[0] = wide nodes allocated (1: the root), counters[1] = size of
+// the next frontier (0); front0[0] = (binary root 0, wide node 0).
+__global__ void __launch_bounds__( 128 ) k_wide_all( int2* front0, int2* front1, int n, int leaf_max, const int2* child, const int2* range, const q4* blo, const q4* bhi, q4* nodes, uint32_t* counters ) {
+	cooperative_groups::grid_group grid = cooperative_groups::this_grid() ;
+	const uint32_t tid = blockIdx.x*blockDim.x+threadIdx.x, stride = gridDim.x*blockDim.x ;
+	int2* fin = front0 ; int2* fout = front1 ;
+	uint32_t n_front = 1 ;
+	while ( n_front ) {
+		for ( uint32_t w = tid ; w<n_front ; w += stride )
+			wide_item( fin[w], n, leaf_max, child, range, blo, bhi, nodes, fout, counters ) ;
+		grid.sync() ;
+		n_front = *reinterpret_cast<volatile uint32_t*>( counters+1 ) ;
+		grid.sync() ;
+		if ( tid == 0 ) counters[1] = 0 ;
+		grid.sync() ;
+		int2* t = fin ; fin = fout ; fout = t ;
 	}
 }
 
