@@ -26,7 +26,7 @@ using namespace rtx ;
 #define RTX_DEFAULT_KERNEL 0            // 0: k_render (one ray per lane, state in registers), 1: k_render_q (compacting ray pool); RTX_KERNEL=reg|q overrides
 #endif
 #ifndef RTX_Q_DEFAULT_CARVEOUT
-#define RTX_Q_DEFAULT_CARVEOUT 60       // k_render_q: 7 CTAs x 18.5 KB of ray slots fit 60 % of the 228 KB; the rest is L1
+#define RTX_Q_DEFAULT_CARVEOUT 75       // k_render_q: 15 CTAs x 12.9 KB of ray slots (64 slots of 176 bytes + queues) take 196 KB of the 228 KB; 60 %: 12 CTAs, 743 ms against 655
 #endif
 #ifndef RTX_DEFAULT_CARVEOUT
 // 20 render CTAs x (4 KB stack + 1 KB the driver reserves) = 100 KB of shared memory; the rest

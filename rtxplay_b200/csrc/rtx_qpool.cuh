@@ -3,7 +3,7 @@
 // Why (round 2): with one ray bound to one lane (rtx_pool.cuh, RegPool) the warp votes for the
 // step kind most lanes are in and the others wait -- measured on B200: 12.5 of 32 lanes active
 // per instruction, the kernel bound by instruction issue x SIMD efficiency.  Here a warp owns a
-// pool of RTX_QR rays (96) whose state lives in shared memory as 16-byte records any lane can
+// pool of RTX_QR rays (64) whose state lives in shared memory as 16-byte records any lane can
 // pick up; per step kind there is a queue of ray slots, every iteration takes up to 32 rays of
 // the kind that fills the most lanes, advances each by one step and queues it under its new
 // kind.  The scheduling simulator (tests/hostemu emu_warpsim_pool) puts 29 lanes on a node step
@@ -36,7 +36,8 @@ namespace rtx {
 #define RTX_QS 11               // quads per slot record: 6 of state + ( RTX_QS-6 ) of stack
 #endif
 #ifndef RTX_QR
-#define RTX_QR 96               // ray slots per warp (simulator: 64 / 96 / 128 -> 158 / 135 / 131 warp instructions per ray)
+#define RTX_QR 64               // ray slots per warp (simulator: 64 / 96 / 128 -> 158 / 135 / 131 warp instructions per ray; measured on B200 with
+                                // 11-quad records: 56 / 64 / 72 / 96 slots -> 669 / 655 / 660 / 797 ms per frame -- the slots compete with L1 for the 228 KB)
 #endif
 #define RTX_QSTACK ( 2*( RTX_QS-6 ) )   // stack entries per slot in shared memory (10: holds 99.6 % of all pushes of the bench scene)
 #define RTX_QOVF   ( 96-RTX_QSTACK )    // further entries per slot in a global overflow area
@@ -188,7 +189,7 @@ template <class P> RTX_HD int qfinish_step( P& p, int slot, int32_t cur, int32_t
 	p.stq( slot, 0, mkq( ibits( cur ), ibits( sp ), tbest, nodes_w ) ) ;
 	const bool top = bitsu( tris_w ) == 0u ;
 	const int kind = qkind_of( cur, top ) ;
-#if ! defined( RTX_Q_NOPREFETCH )
+#if defined( RTX_Q_PREFETCH )   // (measured: 683 ms per frame with these prefetches, 655 without -- the L1 left beside the slots is too small to hold them)
 	if ( kind == K_NODE )
 		prefetch_line( p.dec( slot, nodes_w )+size_t( cur )*RTX_NODE_RECS ) ;
 	else if ( kind == K_LEAF )

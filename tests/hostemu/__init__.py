@@ -11,15 +11,20 @@ _LIB = None
 
 
 def _make(name):
-    """(Re)build a harness library; a stale but existing one is used when the rebuild fails (a
-    GPU box snapshot may carry fresher sources than libraries and no writable tree)."""
+    """(Re)build a harness library.  When the rebuild fails (a GPU-box snapshot without a writable
+    tree) an existing library is used only if it is not older than the sources it is made from --
+    a stale binary would let the CPU parity tests pass against code that is no longer there."""
     path = os.path.join(_HERE, name)
     r = subprocess.run(["make", "-C", _HERE, name], capture_output=True, text=True)
     if r.returncode != 0:
         if not os.path.exists(path):
             raise RuntimeError("cannot build %s:\n%s" % (name, r.stderr[-2000:]))
+        src_dir = os.path.join(_HERE, "..", "..", "rtxplay_b200", "csrc")
+        srcs = [os.path.join(_HERE, "hostemu.cu")] + [os.path.join(src_dir, f) for f in os.listdir(src_dir) if f.endswith((".cuh", ".h"))]
+        if os.path.getmtime(path) < max(os.path.getmtime(f) for f in srcs):
+            raise RuntimeError("make %s failed and the existing library is older than its sources:\n%s" % (name, r.stderr[-2000:]))
         import warnings
-        warnings.warn("make %s failed, using the existing library:\n%s" % (name, r.stderr[-500:]))
+        warnings.warn("make %s failed, using the existing (up-to-date) library:\n%s" % (name, r.stderr[-500:]))
     return path
 
 
