@@ -10,8 +10,10 @@ from rtxplay_b200 import api, scenes  # noqa: E402
 
 spheres = scenes.book1(seed=1)
 w, h = 64, 48
-for mode, ndiv in (("analytic", None), ("mesh", 2)):
-    ctx = api.Context(0)
+# (RTX_KERNEL=q in the environment runs the same through the compacting-pool kernel; the second pass
+#  of each scene goes through a two-replica context: fan-out, sample split, fused reduce + resolve)
+for mode, ndiv, devices in (("analytic", None, None), ("mesh", 2, None), ("mesh", 2, [0, 0])):
+    ctx = api.Context(0) if devices is None else api.Context(devices=devices)
     scenes.load(ctx, spheres, mode, ndiv)
     ctx.resize(w, h)
     cam = api.camera(aspratio=w / h)
