@@ -88,7 +88,7 @@ __device__ __forceinline__ void red_add_u64( unsigned long long* addr, unsigned 
 // integer atomics: order free, bit-reproducible, and no per-tile buffers.
 #define RTX_POOL_R ( 32*RTX_K )
 #ifndef RTX_STICKY
-#define RTX_STICKY 5           // keep doing node steps while at least this many lanes have one (swept: 4-6 best)
+#define RTX_STICKY 5           // keep doing node steps while at least this many lanes have one (4: 586.7, 5: 582.9, 6: 580.8, 8: 581.3 ms per frame)
 #endif
 #ifndef RTX_MIN_CTAS
 #define RTX_MIN_CTAS 18         // launch bound: 17-20 all compile to 96 registers = 5 warps per scheduler, 20 per SM (24 at 80
@@ -154,12 +154,15 @@ __global__ void RTX_RENDER_BOUNDS k_render( const __grid_constant__ FrameArgs a,
 	const uint32_t lane = threadIdx.x ;
 	const uint32_t lt = ( 1u<<lane )-1u ;
 #if defined( RTX_REGPOOL )
-	__shared__ uint32_t stack_words[2*RTX_POOL_STACK*32] ;
+	__shared__ __align__( 8 ) uint32_t stack_words[2*RTX_POOL_STACK*32] ;
 	RegPool p ;
-	p.stk = uint32_t( __cvta_generic_to_shared( stack_words+lane ) ) ;
+	p.stk = uint32_t( __cvta_generic_to_shared( stack_words+2*lane ) ) ;   // 8 bytes per lane and entry: a row of the stack is 256 bytes, one 64-bit access per lane
 	__shared__ uint32_t cold_words[( RTX_COLD_WORDS>0 ? RTX_COLD_WORDS : 1 )*32] ;
 	p.cold = uint32_t( __cvta_generic_to_shared( cold_words+lane ) ) ;
-	p.ovf = ovf_all+( size_t( blockIdx.x )*RTX_POOL_R+lane )*RTX_POOL_OVF*2 ;
+	p.ovf_all = ovf_all ;
+#if ! RTX_OVF_LAZY
+	p.ovf_ = ovf_all+( size_t( blockIdx.x )*RTX_POOL_R+lane )*RTX_POOL_OVF*2 ;
+#endif
 	p.fault = a.S.fault ;
 #else
 	__shared__ uint32_t words[F_WORDS*RTX_POOL_R] ;
@@ -222,6 +225,15 @@ __global__ void RTX_RENDER_BOUNDS k_render( const __grid_constant__ FrameArgs a,
 			case K_NODE: {
 				// node steps dominate: stay with them (one ballot per step instead of a full
 				// vote) while enough lanes still have one
+#if RTX_K == 1 && ! defined( RTX_DEVICE_COUNTERS ) && ! defined( RTX_STICKY_GENERIC )
+				// (one ray per lane: the loop tests the lane's kind, no slot index)
+				do {
+					if ( kinds[0] == K_NODE )
+						kinds[0] = step_node( p, int( lane ), a.S ) ;
+				} while ( __popc( __ballot_sync( 0xffffffffu, kinds[0] == K_NODE ) )>=RTX_STICKY ) ;
+				j = -1 ;
+				break ;
+#endif
 				int jn = j ;
 				while ( true ) {
 					RTX_COUNT_STEP( K_NODE, __ballot_sync( 0xffffffffu, jn>=0 ) ) ;

@@ -46,6 +46,9 @@ namespace rtx {
 #define RTX_SHADE_INLINE 1      // shading frame and scattering inline on thing records fetched with 256-bit loads (rtx_core.cuh qframe_of / qscatter) instead of the
                                 // __noinline__ frame_of / scatter, whose structures travel through local memory (54 LDL/STL + 29 narrow LDG per segment in the r1 profile)
 #endif
+#ifndef RTX_OVF_LAZY
+#define RTX_OVF_LAZY 0          // 1: the lane's overflow-stack address computed in (out-of-line) deep push / pop functions instead of at the top of the loop -- measured slower, 591 against 582 ms per frame
+#endif
 #ifndef RTX_PREFETCH
 #define RTX_PREFETCH 0          // L1 prefetches beyond the first line of the next leaf (bits: 1 its second line, 2 / 4 the second-nearest child when a leaf / a node)
 #endif
@@ -137,9 +140,17 @@ __device__ __forceinline__ constexpr int cold_slot( int fld ) {
 #define RTX_COLD_WORDS ( cold_slot( -1 ) )
 struct RegPool {
 	uint32_t  r[F_STACK] ;
-	uint32_t  stk ;    // shared-space byte address of this lane's stack column (entry i at stk + i*256: ref, +128: distance)
+	uint32_t  stk ;    // shared-space byte address of this lane's stack column (entry i = the 8 bytes (ref, distance) at stk + i*256)
 	uint32_t  cold ;   // shared-space byte address of this lane's column of cold fields (field s at cold + s*128)
-	int32_t*  ovf ;    // this lane's overflow entries (pairs)
+	int32_t*  ovf_all ; // overflow entries (pairs) of all lanes of the grid; this lane's: ovf() (computed where it is needed -- the rare deep stack -- instead of living in two registers)
+#if RTX_OVF_LAZY
+	__device__ __forceinline__ int32_t* ovf() const { return ovf_all+( size_t( blockIdx.x )*32u+threadIdx.x )*RTX_POOL_OVF*2 ; }   // (one ray per lane: 32 columns per CTA)
+#define RTX_DEEP_FN __noinline__
+#else
+	int32_t*  ovf_ ;
+	__device__ __forceinline__ int32_t* ovf() const { return ovf_ ; }
+#define RTX_DEEP_FN __forceinline__
+#endif
 	uint32_t* fault ;  // SceneDev::fault
 	__device__ __forceinline__ uint32_t ldc( int s ) const { uint32_t v ; asm volatile( "ld.shared.u32 %0, [%1];" : "=r"( v ) : "r"( cold+uint32_t( s )*128u ) : "memory" ) ; return v ; }
 	__device__ __forceinline__ void     stc( int s, uint32_t v ) { asm volatile( "st.shared.u32 [%0], %1;" :: "r"( cold+uint32_t( s )*128u ), "r"( v ) : "memory" ) ; }
@@ -150,10 +161,20 @@ struct RegPool {
 	__device__ __forceinline__ void     push( int, int32_t& sp, int32_t v, float t ) {
 		if ( sp<RTX_POOL_STACK ) {
 			const uint32_t a = stk+uint32_t( sp )*256u ;
-			asm volatile( "st.shared.u32 [%0], %1;\n\tst.shared.f32 [%0+128], %2;" :: "r"( a ), "r"( v ), "f"( t ) : "memory" ) ;
-		} else if ( sp<RTX_POOL_STACK+RTX_POOL_OVF ) { ovf[2*( sp-RTX_POOL_STACK )] = v ; ovf[2*( sp-RTX_POOL_STACK )+1] = __float_as_int( t ) ; }
-		else stack_fault( fault ) ;
+			asm volatile( "st.shared.v2.b32 [%0], {%1,%2};" :: "r"( a ), "r"( v ), "r"( __float_as_int( t ) ) : "memory" ) ;
+		} else push_deep( sp, v, t ) ;
 		sp++ ;
+	}
+	// (the rare deep part of the stack, out of line: inlined, its address arithmetic is hoisted to the top of the kernel's loop)
+	__device__ RTX_DEEP_FN void push_deep( int32_t sp, int32_t v, float t ) {
+		if ( sp<RTX_POOL_STACK+RTX_POOL_OVF ) { int32_t* o = ovf() ; o[2*( sp-RTX_POOL_STACK )] = v ; o[2*( sp-RTX_POOL_STACK )+1] = __float_as_int( t ) ; }
+		else stack_fault( fault ) ;
+	}
+	__device__ RTX_DEEP_FN int32_t pop_deep( int32_t sp, float& t ) {
+		if ( sp>=RTX_POOL_STACK+RTX_POOL_OVF ) { t = 0.f ; return RTX_STK_DONE ; }
+		const int32_t* o = ovf() ;
+		t = __int_as_float( o[2*( sp-RTX_POOL_STACK )+1] ) ;
+		return o[2*( sp-RTX_POOL_STACK )] ;
 	}
 #if RTX_FAST_PUSH
 	// the up to three pushes of a node step (children sorted by distance, misses = +inf last) as
@@ -164,17 +185,17 @@ struct RegPool {
 			const uint32_t a = stk+uint32_t( sp )*256u ;
 			uint32_t n ;
 			asm volatile( "{\n\t.reg .pred q3, q2, q1;\n\t.reg .u32 a2, a1, k;\n\t"
-				"setp.lt.f32 q3, %7, 0f7F800000;\n\t"
-				"setp.lt.f32 q2, %5, 0f7F800000;\n\t"
-				"setp.lt.f32 q1, %3, 0f7F800000;\n\t"
-				"@q3 st.shared.u32 [%1], %6;\n\t@q3 st.shared.f32 [%1+128], %7;\n\t"
+				"setp.lt.s32 q3, %7, 0x7F800000;\n\t"     // (entry distances are positive floats or +inf: compare the bit patterns)
+				"setp.lt.s32 q2, %5, 0x7F800000;\n\t"
+				"setp.lt.s32 q1, %3, 0x7F800000;\n\t"
+				"@q3 st.shared.v2.b32 [%1], {%6,%7};\n\t"
 				"selp.u32 k, 256, 0, q3;\n\tadd.u32 a2, %1, k;\n\t"
-				"@q2 st.shared.u32 [a2], %4;\n\t@q2 st.shared.f32 [a2+128], %5;\n\t"
+				"@q2 st.shared.v2.b32 [a2], {%4,%5};\n\t"
 				"selp.u32 k, 256, 0, q2;\n\tadd.u32 a1, a2, k;\n\t"
-				"@q1 st.shared.u32 [a1], %2;\n\t@q1 st.shared.f32 [a1+128], %3;\n\t"
+				"@q1 st.shared.v2.b32 [a1], {%2,%3};\n\t"
 				"selp.u32 k, 256, 0, q1;\n\tadd.u32 a1, a1, k;\n\t"
 				"sub.u32 %0, a1, %1;\n\t}"
-				: "=r"( n ) : "r"( a ), "r"( c1 ), "f"( t1 ), "r"( c2 ), "f"( t2 ), "r"( c3 ), "f"( t3 ) : "memory" ) ;
+				: "=r"( n ) : "r"( a ), "r"( c1 ), "r"( __float_as_int( t1 ) ), "r"( c2 ), "r"( __float_as_int( t2 ) ), "r"( c3 ), "r"( __float_as_int( t3 ) ) : "memory" ) ;
 			sp += int32_t( n>>8 ) ;
 		} else {
 			if ( t3<INFINITY ) push( slot, sp, c3, t3 ) ;
@@ -187,13 +208,12 @@ struct RegPool {
 		sp-- ;
 		if ( sp<RTX_POOL_STACK ) {
 			const uint32_t a = stk+uint32_t( sp )*256u ;
-			int32_t v ;
-			asm volatile( "ld.shared.u32 %0, [%2];\n\tld.shared.f32 %1, [%2+128];" : "=r"( v ), "=f"( t ) : "r"( a ) : "memory" ) ;
+			int32_t v, tb ;
+			asm volatile( "ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"( v ), "=r"( tb ) : "r"( a ) : "memory" ) ;
+			t = __int_as_float( tb ) ;
 			return v ;
 		}
-		if ( sp>=RTX_POOL_STACK+RTX_POOL_OVF ) { t = 0.f ; return RTX_STK_DONE ; }
-		t = __int_as_float( ovf[2*( sp-RTX_POOL_STACK )+1] ) ;
-		return ovf[2*( sp-RTX_POOL_STACK )] ;
+		return pop_deep( sp, t ) ;
 	}
 } ;
 #endif
@@ -231,10 +251,24 @@ RTX_HD void prefetch_line( const void* a ) {
 
 // kind of the work item `cur` for a ray at the top level (level < 0) or inside a mesh
 RTX_HD int kind_of( int32_t cur, int32_t level ) {
+#if defined( __CUDA_ARCH__ ) && ! defined( RTX_KIND_BRANCHY )
+	// three selects (the compiler turns the chain of returns below into three divergent branches at the end of every step)
+	int k ;
+	asm( "{\n\t.reg .pred pn, pd;\n\t.reg .s32 l;\n\t"
+		"setp.lt.u32 pn, %1, %3;\n\t"
+		"setp.eq.s32 pd, %1, %4;\n\t"
+		"shr.u32 l, %2, 31;\n\tadd.s32 l, l, 2;\n\t"      // K_LEAF = 2, K_THING = 3 (level < 0)
+		"selp.s32 l, 4, l, pd;\n\t"                        // K_SHADE
+		"selp.s32 %0, 1, l, pn;\n\t}"                      // K_NODE
+		: "=r"( k ) : "r"( cur ), "r"( level ), "n"( RTX_REF_EMPTY ), "n"( RTX_STK_DONE ) ) ;
+	return k ;
+#else
 	if ( uint32_t( cur )<uint32_t( RTX_REF_EMPTY ) ) return K_NODE ;
 	if ( cur == RTX_STK_DONE ) return K_SHADE ;
 	return level<0 ? K_THING : K_LEAF ;
+#endif
 }
+static_assert( K_NODE == 1 && K_LEAF == 2 && K_THING == 3 && K_SHADE == 4, "kind_of's selects are written for these values" ) ;
 
 // world-space traversal state of a fresh ray
 template <class P> RTX_HD void begin_ray( P& p, int slot, const SceneDev& S, const f3& o, const f3& d ) {
@@ -305,6 +339,14 @@ template <class P> RTX_HD int finish_step( P& p, int slot, int32_t cur, int32_t 
 		prefetch_line( ldp<P, q4>( p, F_NODES0, slot )+size_t( cur )*RTX_NODE_RECS ) ;
 	else
 #endif
+#if defined( __CUDA_ARCH__ ) && ! defined( RTX_KIND_BRANCHY ) && ! ( RTX_PREFETCH & 1 )
+	{
+		// the first triangle of a leaf: one predicated prefetch, the address computed by every lane (no branch)
+		const q4* T = ldp<P, q4>( p, F_TRIS0, slot )+size_t( uint32_t( ~cur )>>3 )*RTX_TRI_RECS ;
+		asm volatile( "{\n\t.reg .pred pl;\n\tsetp.eq.s32 pl, %1, 2;\n\t@pl prefetch.global.L1 [%0];\n\t}" :: "l"( T ), "r"( kind ) ) ;
+		return kind ;
+	}
+#endif
 	if ( kind == K_LEAF ) {
 		const q4* T = ldp<P, q4>( p, F_TRIS0, slot )+size_t( uint32_t( ~cur )>>3 )*RTX_TRI_RECS ;
 		prefetch_line( T ) ;
@@ -340,6 +382,16 @@ template <class P> RTX_HD int step_node( P& p, int slot, const SceneDev& S ) {
 #endif
 	const o8 n01 = ldo( n ), n23 = ldo( n+2 ), n45 = ldo( n+4 ), n67 = ldo( n+6 ) ;
 	const q4 lx = n01.a, ly = n01.b, lz = n23.a, hx = n23.b, hy = n45.a, hz = n45.b, rf = n67.a ;
+#if defined( RTX_EXPERIMENT_EXTRA_LDG ) && defined( __CUDA_ARCH__ )
+	// (timing experiment: 2 x RTX_EXPERIMENT_EXTRA_LDG more loads from the node just read -- L1 hits by construction -- on top of
+	// the four of a node step: 591.5 -> 641.8 (+2 loads) -> 652.8 ms (+4 loads) per frame)
+#pragma unroll
+	for ( int e_ = 0 ; e_<RTX_EXPERIMENT_EXTRA_LDG ; e_++ ) {
+		float x0, x1, x2, x3 ;   // (a plain load: ptxas folds a second .nc load of the same address into the first)
+		asm volatile( "ld.global.ca.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"( x0 ), "=f"( x1 ), "=f"( x2 ), "=f"( x3 ) : "l"( n+2*( e_&3 ) ) : "memory" ) ;
+		if ( x0 == 1.234567e-30f && x3 == 7.654321e-31f ) stack_fault( p.fault ) ;   // (keeps the load alive; never true)
+	}
+#endif
 	int32_t c0 = asint( rf.x ), c1 = asint( rf.y ), c2 = asint( rf.z ), c3 = asint( rf.w ) ;
 #if RTX_FFMA2 && defined( __CUDA_ARCH__ )
 	float t0, t1, t2, t3 ;
@@ -353,7 +405,15 @@ template <class P> RTX_HD int step_node( P& p, int slot, const SceneDev& S ) {
 	// (unused child slots hold the box lo = hi = +inf, which no ray enters: no test needed)
 	// nearest child next, the others pushed far to near (a cheaper "nearest only" ordering was
 	// measured: 902 ms instead of 814 ms per frame -- the order of the pushed children matters)
-#if ! defined( RTX_SORT_MINMAX )
+#if defined( RTX_SORT_SELP ) && defined( __CUDA_ARCH__ )
+	// (measured alternative: compare-exchange as one comparison and four selects -- 26 instead of 36 instructions for the
+	// network, all of them on the ALU pipe: 596.4 against 591.6 ms per frame for the predicated moves the compiler spreads over
+	// the ALU and FMA pipes)
+#define RTX_CSWAP( ta, ca, tb, cb ) asm( "{\n\t.reg .pred p;\n\t.reg .f32 x;\n\t.reg .b32 y;\n\t" \
+	"setp.lt.f32 p, %2, %0;\n\t" \
+	"selp.f32 x, %2, %0, p;\n\tselp.f32 %2, %0, %2, p;\n\tmov.f32 %0, x;\n\t" \
+	"selp.b32 y, %3, %1, p;\n\tselp.b32 %3, %1, %3, p;\n\tmov.b32 %1, y;\n\t}" : "+f"( ta ), "+r"( ca ), "+f"( tb ), "+r"( cb ) ) ;
+#elif ! defined( RTX_SORT_MINMAX )
 #define RTX_CSWAP( ta, ca, tb, cb ) if ( tb<ta ) { const float tt = ta ; ta = tb ; tb = tt ; const int32_t cc = ca ; ca = cb ; cb = cc ; }
 #else
 	// (measured alternative: compare-exchange as min / max on the distances and two selects on the references --
@@ -365,6 +425,17 @@ template <class P> RTX_HD int step_node( P& p, int slot, const SceneDev& S ) {
 	if ( t0 == INFINITY )
 		cur = pop_next( p, slot, S, sp, level ) ;
 	else {
+#if RTX_PREFETCH & 16
+		// the nearest child is the next step's node: ask for its line now, ahead of the pushes and the vote (bit 32: all four
+		// 32-byte sectors).  Measured: 586.5 (one prefetch) and 651.3 ms (four) against 582.9 ms per frame without
+		if ( uint32_t( c0 )<uint32_t( RTX_REF_EMPTY ) ) {
+			const q4* nn = ldp<P, q4>( p, F_NODES0, slot )+size_t( c0 )*RTX_NODE_RECS ;
+			prefetch_line( nn ) ;
+#if RTX_PREFETCH & 32
+			prefetch_line( nn+2 ) ; prefetch_line( nn+4 ) ; prefetch_line( nn+6 ) ;
+#endif
+		}
+#endif
 		push_far_children( p, slot, sp, c1, t1, c2, t2, c3, t3 ) ;
 #if RTX_PREFETCH & 2
 		// the second-nearest child, when it is a mesh leaf, is usually next but one: fetch its triangles now
