@@ -225,6 +225,30 @@ def test_postproc_matches_reference_transfer(spheres):
     ctx.close()
 
 
+@pytest.mark.parametrize("mode,ndiv,w,h,spp,variant", [("analytic", None, 150, 100, 4, api.VARIANT_RTOW), ("mesh", 2, 96, 64, 3, api.VARIANT_RTWO_I), ("mesh", None, 120, 80, 2, api.VARIANT_RTOW)])
+def test_pool_kernel_equals_register_kernel(spheres, monkeypatch, mode, ndiv, w, h, spp, variant):
+    """The compacting ray pool kernel (`RTX_KERNEL=q` at rtx_init) schedules the same
+    step functions differently: radiance sums, segment counts and guide sums equal those of the default
+    kernel bit for bit -- on analytic spheres (also against the oracle's float mirror), on a small mesh
+    scene with the iterative variant, and on the benchmarked mesh mix (8.8 M instanced triangles)."""
+    frames = {}
+    for kernel in ("reg", "q"):
+        monkeypatch.setenv("RTX_KERNEL", kernel)
+        ctx, tab, meshes = _ctx(spheres, mode, ndiv)
+        cam = api.camera(aspratio=w / h)
+        ctx.resize(w, h)
+        ctx.render(ctx.params(cam, spp, guides=1, variant=variant))
+        assert ctx.frame_stats()["kernel"] == (1 if kernel == "q" else 0)
+        frames[kernel] = (ctx.read(api.BUF_ACCUM), ctx.read(api.BUF_GUIDE_ACC), ctx.read(api.BUF_RAWRGB), ctx.stats()["segments"])
+        ctx.close()
+    for a, b in zip(frames["reg"], frames["q"]):
+        assert np.array_equal(a, b)
+    if mode == "analytic":
+        ref = orc.render(orc.F32_PCG, tab, api.camera_table(cam), w, h, spp, 50, meshes=meshes)
+        assert np.array_equal(frames["q"][0][..., :3], ref["fix"])
+        assert np.array_equal(frames["q"][0][..., 3].astype(np.uint32), ref["rpp"])
+
+
 @pytest.mark.parametrize("mode,ndiv", [("analytic", None), ("mesh", 2)])
 def test_guide_layers(spheres, mode, ndiv):
     """Denoiser guide layers (optx/camera_i.cu:99-113, optx/optics_i.cu:97-101, 185-189): per-pixel
