@@ -269,9 +269,13 @@ void lbvh_build( rtx_ctx* c, Lbvh& b, const q4* plo, const q4* phi, uint32_t n, 
 	int* bounds = talloc<int>( c, 6 ) ;
 	uint64_t* keys0 = talloc<uint64_t>( c, n ) ; uint64_t* keys1 = talloc<uint64_t>( c, n ) ;
 	uint32_t* vals1 = talloc<uint32_t>( c, n ) ;
+#if ! RTX_SORT_ONESWEEP
 	uint32_t* counts = talloc<uint32_t>( c, size_t( 256 )*nblocks ) ;
 	const uint32_t n_chunks = ( 256u*nblocks+RTX_SCAN_CHUNK-1u )/RTX_SCAN_CHUNK ;   // count-table scan: one block up to 16 K counters, else chunked
 	uint32_t* chunk_sums = talloc<uint32_t>( c, n_chunks ) ;
+#else
+	( void ) nblocks ;
+#endif
 
 	CK( cudaEventRecord( c->stage_ev[0], c->stream ) ) ;
 	k_bounds_init<<<1, 32, 0, c->stream>>>( bounds ) ;
@@ -281,6 +285,24 @@ void lbvh_build( rtx_ctx* c, Lbvh& b, const q4* plo, const q4* phi, uint32_t n, 
 	CK( cudaEventRecord( c->stage_ev[1], c->stream ) ) ;
 	uint64_t* kin = keys0 ; uint64_t* kout = keys1 ;
 	uint32_t* vin = b.order ; uint32_t* vout = vals1 ;
+#if RTX_SORT_ONESWEEP
+	// one read and one write of every key per digit: all eight histograms first, then one
+	// look-back pass per digit (rtx_lbvh.cuh)
+	const uint32_t ntiles = ( n+RTX_OS_TILE-1u )/RTX_OS_TILE ;
+	uint32_t* os_hist = talloc<uint32_t>( c, 8*256+8 ) ;      // [8][256] counts -> bucket starts, then the eight tile tickets
+	uint32_t* os_status = talloc<uint32_t>( c, size_t( 256 )*ntiles ) ;
+	CK( cudaMemsetAsync( os_hist, 0, sizeof( uint32_t )*( 8*256+8 ), c->stream ) ) ;
+	k_radix_hist8<<<std::min( 1184u, ( n+255u )/256u ), 256, 0, c->stream>>>( keys0, n, os_hist ) ;
+	k_radix_bases<<<8, 256, 0, c->stream>>>( os_hist ) ;
+	c->launches += 2 ;
+	for ( int pass = 0 ; pass<8 ; pass++ ) {
+		CK( cudaMemsetAsync( os_status, 0, sizeof( uint32_t )*size_t( 256 )*ntiles, c->stream ) ) ;
+		k_radix_onesweep<<<ntiles, RTX_OS_THREADS, 0, c->stream>>>( kin, vin, n, 8*pass, os_hist+256*pass, os_status, os_hist+8*256+pass, kout, vout ) ;
+		c->launches += 1 ;
+		std::swap( kin, kout ) ; std::swap( vin, vout ) ;
+	}
+	tfree( c, os_hist, 8*256+8 ) ; tfree( c, os_status, size_t( 256 )*ntiles ) ;
+#else
 	for ( int pass = 0 ; pass<8 ; pass++ ) {
 		const int shift = 8*pass ;
 		k_radix_hist<<<nblocks, 32*RTX_RS_WARPS, 0, c->stream>>>( kin, n, shift, counts, nblocks ) ;
@@ -295,6 +317,7 @@ void lbvh_build( rtx_ctx* c, Lbvh& b, const q4* plo, const q4* phi, uint32_t n, 
 		c->launches += 3 ;
 		std::swap( kin, kout ) ; std::swap( vin, vout ) ;
 	}
+#endif
 	// 8 passes: the sorted data is back in keys0 / b.order
 	CK( cudaEventRecord( c->stage_ev[2], c->stream ) ) ;
 	if ( n>1 ) {
@@ -305,7 +328,10 @@ void lbvh_build( rtx_ctx* c, Lbvh& b, const q4* plo, const q4* phi, uint32_t n, 
 	lbvh_refit( c, b, plo, phi, leaf_max ) ;
 	c->stage_full = true ;
 
-	tfree( c, bounds, 6 ) ; tfree( c, keys0, n ) ; tfree( c, keys1, n ) ; tfree( c, vals1, n ) ; tfree( c, counts, size_t( 256 )*nblocks ) ; tfree( c, chunk_sums, n_chunks ) ;
+	tfree( c, bounds, 6 ) ; tfree( c, keys0, n ) ; tfree( c, keys1, n ) ; tfree( c, vals1, n ) ;
+#if ! RTX_SORT_ONESWEEP
+	tfree( c, counts, size_t( 256 )*nblocks ) ; tfree( c, chunk_sums, n_chunks ) ;
+#endif
 	if ( ! keep_binary ) {
 		// a mesh is never refitted: drop the binary tree and trim the node array
 		lbvh_free_binary( c, b ) ;
@@ -676,7 +702,8 @@ int rtx_init( int device, rtx_ctx** out ) {
 			const void* kernels[] = { ( const void* ) k_render<false>, ( const void* ) k_render<true>, ( const void* ) k_primary_hits, ( const void* ) k_trace_rays, ( const void* ) k_pick,
 				( const void* ) k_resolve, ( const void* ) k_resolve_guides, ( const void* ) k_postproc, ( const void* ) k_sum_segments, ( const void* ) k_tri_bounds, ( const void* ) k_thing_bounds,
 				( const void* ) k_bounds_init, ( const void* ) k_bounds_reduce, ( const void* ) k_morton, ( const void* ) k_radix_hist, ( const void* ) k_radix_scan,
-				( const void* ) k_radix_scatter, ( const void* ) k_karras, ( const void* ) k_refit, ( const void* ) k_wide_level, ( const void* ) k_wide_all, ( const void* ) k_scan_chunks, ( const void* ) k_scan_add, ( const void* ) k_pack_tris } ;
+				( const void* ) k_radix_scatter, ( const void* ) k_karras, ( const void* ) k_refit, ( const void* ) k_wide_level, ( const void* ) k_wide_all, ( const void* ) k_scan_chunks, ( const void* ) k_scan_add, ( const void* ) k_pack_tris,
+				( const void* ) k_radix_hist8, ( const void* ) k_radix_bases, ( const void* ) k_radix_onesweep } ;
 			for ( const void* k : kernels ) CK( cudaFuncGetAttributes( &fa, k ) ) ;
 		}
 		// the render kernel is persistent: one warp per CTA, as many CTAs as fit

@@ -2,9 +2,11 @@
 // a mesh and :258-270 / :281-293 for the instance level).  All hand-written, no CUB:
 //   k_bounds_reduce   centroid bounds of the primitives (ordered-int atomics)
 //   k_morton          63-bit Morton key (21 bits/axis) of each primitive centroid
-//   k_radix_hist / k_radix_scan / k_radix_scatter
-//                     stable LSD radix sort, 8-bit digits, one warp per tile, ranks from
-//                     __match_any_sync
+//   k_radix_hist8 / k_radix_bases / k_radix_onesweep
+//                     stable LSD radix sort, 8-bit digits, one kernel per digit: tile prefixes
+//                     by decoupled look-back, ranks from __match_any_sync, coalesced bucket runs
+//                     (k_radix_hist / k_radix_scan / k_radix_scatter: the count / scan /
+//                     scatter passes it replaced, -DRTX_SORT_ONESWEEP=0)
 //   k_karras          Karras 2012 radix-tree hierarchy over the sorted keys (ties broken
 //                     by position)
 //   k_refit           bottom-up AABB refit with per-node arrival counters
@@ -169,6 +171,9 @@ __global__ void __launch_bounds__( 256 ) k_morton( const q4* plo, const q4* phi,
 // offsets, k_radix_scatter re-counts per warp, offsets each warp behind the warps before it
 // and ranks the keys of a 32-key round with __match_any_sync (stable: rounds in order, lanes
 // in order).
+#ifndef RTX_SORT_ONESWEEP
+#define RTX_SORT_ONESWEEP 1   // 0: this three-kernel pass (count, scan, scatter); 1: the one-sweep pass further down
+#endif
 #define RTX_RS_TILE   2048   // keys per CTA
 #define RTX_RS_WARPS  4
 #define RTX_RS_ROUNDS ( RTX_RS_TILE/RTX_RS_WARPS/32 )   // 32-key rounds per warp
@@ -281,6 +286,177 @@ __global__ void __launch_bounds__( 32*RTX_RS_WARPS ) k_radix_scatter( const uint
 			keys_out[pos] = key[r] ;
 			vals_out[pos] = val[r] ;
 		}
+	}
+}
+
+// ---- radix sort, one sweep per digit ---------------------------------------------------
+// The same stable LSD sort with every key read once per pass (the sort above reads it twice and
+// writes element by element).  k_radix_hist8 counts all eight digits of every key in one read;
+// k_radix_bases turns each digit's 256 counts into the global start of its bucket; one launch of
+// k_radix_onesweep per digit then does the rest: a CTA draws the next tile of RTX_OS_TILE keys
+// (ticket: a tile's predecessors are always resident or done), ranks its keys per warp with
+// __match_any_sync (rounds in order, lanes in order: stable), learns where its tile starts in
+// every bucket by looking back over the tiles before it (decoupled look-back: a status word per
+// tile and digit holds the tile's own count first, the inclusive count once it is known; thread d
+// handles digit d), moves keys and values through shared memory into bucket order and writes
+// each bucket's run with consecutive threads on consecutive addresses.
+#define RTX_OS_THREADS 256
+#define RTX_OS_ITEMS   16
+#define RTX_OS_TILE    ( RTX_OS_THREADS*RTX_OS_ITEMS )   // 4096 keys per tile
+#define RTX_OS_WARPS   ( RTX_OS_THREADS/32 )
+#define RTX_OS_AGG     0x40000000u    // status: the tile's own count ...
+#define RTX_OS_INCL    0x80000000u    // ... the count of all tiles up to and including it
+#define RTX_OS_COUNT   0x3fffffffu
+
+__global__ void __launch_bounds__( 256 ) k_radix_hist8( const uint64_t* keys, uint32_t n, uint32_t* hist ) {
+	__shared__ uint32_t h[8*256] ;
+	for ( int i = threadIdx.x ; i<8*256 ; i += 256 ) h[i] = 0 ;
+	__syncthreads() ;
+	const uint32_t lane = threadIdx.x&31u ;
+	// (whole warps stay in the loop so that the warp votes below are complete)
+	for ( uint32_t i0 = ( blockIdx.x*256u+( threadIdx.x&~31u ) ) ; i0<n ; i0 += gridDim.x*256u ) {
+		const uint32_t i = i0+lane ;
+		const bool act = i<n ;
+		const uint64_t key = act ? keys[i] : 0ull ;
+		const uint32_t mask = __ballot_sync( 0xffffffffu, act ) ;
+		if ( act ) {
+#pragma unroll
+			for ( int p = 0 ; p<8 ; p++ ) {
+				const uint32_t d = uint32_t( key>>( 8*p ) )&255u ;
+				// neighbouring primitives share their high digits: one add for the warp then
+				int same ;
+				__match_all_sync( mask, d, &same ) ;
+				if ( same ) { if ( lane == uint32_t( __ffs( mask )-1 ) ) atomicAdd( h+256*p+d, uint32_t( __popc( mask ) ) ) ; }
+				else atomicAdd( h+256*p+d, 1u ) ;
+			}
+		}
+	}
+	__syncthreads() ;
+	for ( int i = threadIdx.x ; i<8*256 ; i += 256 ) if ( h[i] ) atomicAdd( hist+i, h[i] ) ;
+}
+// hist[8][256] -> exclusive scan of every row (block p: digit p), in place
+__global__ void __launch_bounds__( 256 ) k_radix_bases( uint32_t* hist ) {
+	__shared__ uint32_t part[256] ;
+	uint32_t* row = hist+256*blockIdx.x ;
+	const uint32_t c = row[threadIdx.x] ;
+	part[threadIdx.x] = c ;
+	__syncthreads() ;
+	for ( int o = 1 ; o<256 ; o <<= 1 ) {
+		const uint32_t v = threadIdx.x>=o ? part[threadIdx.x-o] : 0u ;
+		__syncthreads() ;
+		part[threadIdx.x] += v ;
+		__syncthreads() ;
+	}
+	row[threadIdx.x] = part[threadIdx.x]-c ;
+}
+__global__ void __launch_bounds__( RTX_OS_THREADS, 3 ) k_radix_onesweep( const uint64_t* keys, const uint32_t* vals, uint32_t n, int shift, const uint32_t* bases, uint32_t* status, uint32_t* ticket, uint64_t* keys_out, uint32_t* vals_out ) {
+	__shared__ uint32_t wh[RTX_OS_WARPS][256] ;     // per warp and digit: count, then offset inside the tile's run of the digit
+	__shared__ uint32_t tile_start[256] ;          // first position of the digit's run in the tile's bucket order
+	__shared__ uint32_t gbase[256] ;               // where that run goes in the output
+	__shared__ uint32_t wsum[RTX_OS_WARPS] ;
+	__shared__ uint32_t s_tile ;
+	__shared__ uint64_t stage[RTX_OS_TILE] ;
+	const uint32_t tid = threadIdx.x, lane = tid&31u, warp = tid>>5 ;
+	if ( tid == 0 ) s_tile = atomicAdd( ticket, 1u ) ;
+	for ( int d = tid ; d<256*RTX_OS_WARPS ; d += RTX_OS_THREADS ) ( &wh[0][0] )[d] = 0 ;
+	__syncthreads() ;
+	const uint32_t tile = s_tile ;
+	const uint32_t tile0 = tile*RTX_OS_TILE ;
+	const uint32_t base = tile0+warp*( RTX_OS_TILE/RTX_OS_WARPS ) ;
+	uint64_t key[RTX_OS_ITEMS] ;
+	uint32_t val[RTX_OS_ITEMS], pos[RTX_OS_ITEMS] ;
+#pragma unroll
+	for ( int r = 0 ; r<RTX_OS_ITEMS ; r++ ) {
+		const uint32_t i = base+uint32_t( r )*32u+lane ;
+		key[r] = i<n ? keys[i] : 0ull ;
+		val[r] = i<n ? vals[i] : 0u ;
+	}
+	// ranks inside the warp's run of the tile: the lanes of a round that share a digit find each other
+	// (all rounds' matches first: they are independent), the first of them bumps the warp's counter of
+	// the digit and hands the old value to the others (the atomics of successive rounds queue up in
+	// order -- no round waits for the one before it)
+#pragma unroll
+	for ( int r = 0 ; r<RTX_OS_ITEMS ; r++ ) {
+		const bool act = base+uint32_t( r )*32u+lane<n ;
+		const uint32_t mask = __ballot_sync( 0xffffffffu, act ) ;
+		pos[r] = act ? __match_any_sync( mask, uint32_t( key[r]>>shift )&255u ) : 0u ;
+	}
+#pragma unroll
+	for ( int r = 0 ; r<RTX_OS_ITEMS ; r++ ) {
+		const bool act = base+uint32_t( r )*32u+lane<n ;
+		const uint32_t mask = __ballot_sync( 0xffffffffu, act ) ;
+		if ( act ) {
+			const uint32_t peers = pos[r] ;
+			const uint32_t rank = __popc( peers&( ( 1u<<lane )-1u ) ) ;
+			uint32_t old = 0 ;
+			if ( rank == 0 ) old = atomicAdd( &wh[warp][uint32_t( key[r]>>shift )&255u], uint32_t( __popc( peers ) ) ) ;
+			old = __shfl_sync( mask, old, __ffs( peers )-1 ) ;
+			pos[r] = old+rank ;
+		}
+	}
+	__syncthreads() ;
+	// digit tid: the warps' counts -> offsets, the tile's count
+	uint32_t total = 0 ;
+#pragma unroll
+	for ( int w = 0 ; w<RTX_OS_WARPS ; w++ ) { const uint32_t c = wh[w][tid] ; wh[w][tid] = total ; total += c ; }
+	// publish it, then find out how many keys of this digit the tiles in front hold
+	volatile uint32_t* st = status ;
+	if ( tile == 0 ) st[tid] = total|RTX_OS_INCL ;
+	else st[size_t( tile )*256u+tid] = total|RTX_OS_AGG ;
+	// (meanwhile) exclusive scan of the counts over the digits: the tile's bucket order
+	uint32_t incl = total ;
+#pragma unroll
+	for ( int o = 1 ; o<32 ; o <<= 1 ) { const uint32_t v = __shfl_up_sync( 0xffffffffu, incl, o ) ; if ( lane>=uint32_t( o ) ) incl += v ; }
+	if ( lane == 31 ) wsum[warp] = incl ;
+	__syncthreads() ;
+	uint32_t before = 0 ;
+#pragma unroll
+	for ( int w = 0 ; w<RTX_OS_WARPS ; w++ ) if ( uint32_t( w )<warp ) before += wsum[w] ;
+	tile_start[tid] = before+incl-total ;
+	uint32_t front = 0 ;
+	if ( tile>0 ) {
+		uint32_t look = tile-1u ;
+		while ( true ) {
+			const uint32_t v = st[size_t( look )*256u+tid] ;
+			if ( v&RTX_OS_INCL ) { front += v&RTX_OS_COUNT ; break ; }
+			if ( v&RTX_OS_AGG ) { front += v&RTX_OS_COUNT ; look-- ; }   // (tile 0 publishes an inclusive count: the walk ends there at the latest)
+		}
+		st[size_t( tile )*256u+tid] = ( front+total )|RTX_OS_INCL ;
+	}
+	gbase[tid] = bases[tid]+front ;
+	__syncthreads() ;
+	// keys into bucket order, out in runs
+#pragma unroll
+	for ( int r = 0 ; r<RTX_OS_ITEMS ; r++ )
+		if ( base+uint32_t( r )*32u+lane<n ) {
+			const uint32_t d = uint32_t( key[r]>>shift )&255u ;
+			pos[r] += tile_start[d]+wh[warp][d] ;
+			stage[pos[r]] = key[r] ;
+		}
+	__syncthreads() ;
+	const uint32_t n_tile = min( uint32_t( RTX_OS_TILE ), n-tile0 ) ;
+	uint32_t dst[RTX_OS_ITEMS] ;
+#pragma unroll
+	for ( int k = 0 ; k<RTX_OS_ITEMS ; k++ ) {
+		const uint32_t i = uint32_t( k )*RTX_OS_THREADS+tid ;
+		dst[k] = 0 ;
+		if ( i<n_tile ) {
+			const uint64_t kk = stage[i] ;
+			const uint32_t d = uint32_t( kk>>shift )&255u ;
+			dst[k] = gbase[d]+( i-tile_start[d] ) ;
+			keys_out[dst[k]] = kk ;
+		}
+	}
+	__syncthreads() ;
+	uint32_t* sv = reinterpret_cast<uint32_t*>( stage ) ;
+#pragma unroll
+	for ( int r = 0 ; r<RTX_OS_ITEMS ; r++ )
+		if ( base+uint32_t( r )*32u+lane<n ) sv[pos[r]] = val[r] ;
+	__syncthreads() ;
+#pragma unroll
+	for ( int k = 0 ; k<RTX_OS_ITEMS ; k++ ) {
+		const uint32_t i = uint32_t( k )*RTX_OS_THREADS+tid ;
+		if ( i<n_tile ) vals_out[dst[k]] = sv[i] ;
 	}
 }
 

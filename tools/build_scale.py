@@ -41,7 +41,7 @@ if os.path.exists(pk):
     peak = json.load(open(pk))["hbm_gbs"]
 # bytes every stage has to move per primitive (reads + writes of its arrays, each touched once per pass)
 model = {"keys": 32 * 2 + 12,                 # primitive boxes read by the bounds reduction and by the key kernel; key + index written
-         "sort": 8 * (8 + 12 + 12),           # 8 passes: keys read by the histogram; keys + indices read and written by the scatter
+         "sort": 8 + 8 * (12 + 12),           # keys read once for the eight histograms; 8 passes: keys + indices read and written
          "hierarchy": 8 + 16 + 16 + 8,        # sorted keys read; children, ranges, parents written
          "boxes": 4 + 32 + 64 + 64 + 4,       # order, primitive box gathered; leaf + inner boxes written (and read once by the parent); flags
          "wide_nodes": 16 + 64 + 128 / 1.5}   # binary children / ranges / boxes read; one 128-byte node per ~1.5 primitives written
