@@ -70,7 +70,7 @@ typedef struct {
 	uint64_t paths ;
 	float    ms_render ;        /* device time of the path-tracing kernel(s) of the last rtx_render */
 	float    ms_build_blas ;    /* device time of all mesh LBVH builds so far */
-	float    ms_build_tlas ;    /* device time of the last top-level build or refit */
+	float    ms_build_tlas ;    /* device time of the last top-level build or refit (from the upload of the thing records on) */
 	uint32_t launches ;         /* kernels launched by this context so far */
 	uint32_t n_things, n_meshes ;
 	uint64_t n_triangles ;      /* unique triangles stored */

@@ -393,6 +393,9 @@ void upload_things( rtx_ctx* c ) {
 			lo[k] = m.bvh.root_lo ; hi[k] = m.bvh.root_hi ;
 		}
 	}
+	// (the device time of a top-level build or refit starts here: the copies of the thing records, their world bounds,
+	// the hierarchy -- not the host loop above, during which the device idles)
+	CK( cudaEventRecord( c->ev0, c->stream ) ) ;
 	CK( cudaMemcpyAsync( c->d_trav, trav.data(), sizeof( ThingTrav )*n, cudaMemcpyHostToDevice, c->stream ) ) ;
 	CK( cudaMemcpyAsync( c->d_shade, shade.data(), sizeof( ThingShade )*n, cudaMemcpyHostToDevice, c->stream ) ) ;
 	CK( cudaMemcpyAsync( c->d_bsphere, bs.data(), sizeof( q4 )*n, cudaMemcpyHostToDevice, c->stream ) ) ;
@@ -929,8 +932,7 @@ int rtx_thing_set_optics( rtx_ctx* c, uint32_t thing_id, const rtx_optics* optic
 int rtx_accel_build( rtx_ctx* c ) {
 	RTX_TRY( c )
 	CK( cudaSetDevice( c->device ) ) ;
-	CK( cudaEventRecord( c->ev0, c->stream ) ) ;
-	upload_things( c ) ;
+	upload_things( c ) ;   // (records ev0)
 	const uint32_t n = c->n_things_dev ;
 	if ( n ) lbvh_build( c, c->tlas, c->d_tp_lo, c->d_tp_hi, n, 1, true ) ;
 	else     lbvh_free( c, c->tlas ) ;
@@ -948,8 +950,7 @@ int rtx_accel_refit( rtx_ctx* c ) {
 	CK( cudaSetDevice( c->device ) ) ;
 	if ( ! c->built || c->things.size() != c->tlas.n )
 		throw std::runtime_error( "rtx_accel_refit: thing count changed since rtx_accel_build" ) ;
-	CK( cudaEventRecord( c->ev0, c->stream ) ) ;
-	upload_things( c ) ;
+	upload_things( c ) ;   // (records ev0)
 	if ( c->tlas.n ) lbvh_refit( c, c->tlas, c->d_tp_lo, c->d_tp_hi, 1 ) ;
 	CK( cudaEventRecord( c->ev1, c->stream ) ) ;
 	CK( cudaStreamSynchronize( c->stream ) ) ;
