@@ -307,6 +307,16 @@ __global__ void __launch_bounds__( 32*RTX_RS_WARPS ) k_radix_scatter( const uint
 #define RTX_OS_AGG     0x40000000u    // status: the tile's own count ...
 #define RTX_OS_INCL    0x80000000u    // ... the count of all tiles up to and including it
 #define RTX_OS_COUNT   0x3fffffffu
+#ifndef RTX_OS_BALLOT_RANK
+#define RTX_OS_BALLOT_RANK 1          // groups of equal digits from eight ballots (1) or from __match_any_sync (0).  106 M keys, eight
+                                     // passes: ballots 9.6 (2 CTAs per SM) / 10.2 ms (3), match 10.8 / 10.1 ms
+#endif
+#ifndef RTX_OS_MIN_CTAS
+#define RTX_OS_MIN_CTAS 2             // resident CTAs per SM the register budget is cut for (3: 80 registers and spills)
+#endif
+#ifndef RTX_OS_WINDOW
+#define RTX_OS_WINDOW  4              // status words per look-back round trip (1 / 4 / 8 / 16: 10.0 / 10.1 / 10.2 / 10.9 ms: the walk is not what a pass waits for)
+#endif
 
 __global__ void __launch_bounds__( 256 ) k_radix_hist8( const uint64_t* keys, uint32_t n, uint32_t* hist ) {
 	__shared__ uint32_t h[8*256] ;
@@ -349,7 +359,7 @@ __global__ void __launch_bounds__( 256 ) k_radix_bases( uint32_t* hist ) {
 	}
 	row[threadIdx.x] = part[threadIdx.x]-c ;
 }
-__global__ void __launch_bounds__( RTX_OS_THREADS, 3 ) k_radix_onesweep( const uint64_t* keys, const uint32_t* vals, uint32_t n, int shift, const uint32_t* bases, uint32_t* status, uint32_t* ticket, uint64_t* keys_out, uint32_t* vals_out ) {
+__global__ void __launch_bounds__( RTX_OS_THREADS, RTX_OS_MIN_CTAS ) k_radix_onesweep( const uint64_t* keys, const uint32_t* vals, uint32_t n, int shift, const uint32_t* bases, uint32_t* status, uint32_t* ticket, uint64_t* keys_out, uint32_t* vals_out ) {
 	__shared__ uint32_t wh[RTX_OS_WARPS][256] ;     // per warp and digit: count, then offset inside the tile's run of the digit
 	__shared__ uint32_t tile_start[256] ;          // first position of the digit's run in the tile's bucket order
 	__shared__ uint32_t gbase[256] ;               // where that run goes in the output
@@ -379,7 +389,21 @@ __global__ void __launch_bounds__( RTX_OS_THREADS, 3 ) k_radix_onesweep( const u
 	for ( int r = 0 ; r<RTX_OS_ITEMS ; r++ ) {
 		const bool act = base+uint32_t( r )*32u+lane<n ;
 		const uint32_t mask = __ballot_sync( 0xffffffffu, act ) ;
+#if RTX_OS_BALLOT_RANK
+		// the lanes with the same digit, from eight votes (one per digit bit) instead of one __match_any_sync per round,
+		// whose results the warps of a tile queue up for (a quarter of the stall samples of a pass)
+		const uint32_t d = uint32_t( key[r]>>shift )&255u ;
+		uint32_t peers = mask ;
+#pragma unroll
+		for ( int b = 0 ; b<8 ; b++ ) {
+			const bool bit = ( d>>b )&1u ;
+			const uint32_t bal = __ballot_sync( 0xffffffffu, act && bit ) ;
+			peers &= bit ? bal : ~bal ;
+		}
+		pos[r] = act ? peers : 0u ;
+#else
 		pos[r] = act ? __match_any_sync( mask, uint32_t( key[r]>>shift )&255u ) : 0u ;
+#endif
 	}
 #pragma unroll
 	for ( int r = 0 ; r<RTX_OS_ITEMS ; r++ ) {
@@ -415,11 +439,25 @@ __global__ void __launch_bounds__( RTX_OS_THREADS, 3 ) k_radix_onesweep( const u
 	tile_start[tid] = before+incl-total ;
 	uint32_t front = 0 ;
 	if ( tile>0 ) {
-		uint32_t look = tile-1u ;
-		while ( true ) {
-			const uint32_t v = st[size_t( look )*256u+tid] ;
-			if ( v&RTX_OS_INCL ) { front += v&RTX_OS_COUNT ; break ; }
-			if ( v&RTX_OS_AGG ) { front += v&RTX_OS_COUNT ; look-- ; }   // (tile 0 publishes an inclusive count: the walk ends there at the latest)
+		// walk back over the tiles in front, RTX_OS_WINDOW status words per round trip (independent loads), adding own
+		// counts until a tile with an inclusive count turns up (tile 0 publishes one: the walk ends there at the latest);
+		// a word that is not published yet ends the round, the next one starts there
+		int look = int( tile )-1 ;
+		bool found = false ;
+		while ( ! found ) {
+			uint32_t v[RTX_OS_WINDOW] ;
+#pragma unroll
+			for ( int j = 0 ; j<RTX_OS_WINDOW ; j++ ) v[j] = look-j>=0 ? st[size_t( look-j )*256u+tid] : RTX_OS_INCL ;
+			int used = 0 ;
+#pragma unroll
+			for ( int j = 0 ; j<RTX_OS_WINDOW ; j++ )
+				if ( ! found && used == j && ( v[j]&( RTX_OS_INCL|RTX_OS_AGG ) ) ) {
+					front += v[j]&RTX_OS_COUNT ;
+					found = ( v[j]&RTX_OS_INCL ) != 0u ;
+					used = j+1 ;
+				}
+			look -= used ;
+			if ( ! found && used == 0 ) __nanosleep( 64 ) ;
 		}
 		st[size_t( tile )*256u+tid] = ( front+total )|RTX_OS_INCL ;
 	}
