@@ -144,6 +144,43 @@ def test_lbvh_equals_exhaustive_scan_full_scene(spheres):
     ctx.close()
 
 
+def test_big_mesh_hierarchy_equals_exhaustive_scan():
+    """One mesh of 4.2 M triangles (a sphere of ten subdivisions): 1024 tiles of the one-sweep radix
+    sort -- several waves of CTAs, look-back across tiles that are not resident together -- and 14
+    levels of the collapse.  The hierarchy finds what the exhaustive scan finds (ids and t), and
+    the sorted order is a permutation that covers every triangle (each one is hit-able)."""
+    xyz, idx = api.sphere_mesh(1., 10)
+    assert len(idx) == 4 << 20
+    ctx = api.Context(0)
+    m = ctx.add_mesh(xyz, idx)
+    ctx.add_thing(m, api.Optics(api.DIFFUSE, (.5, .5, .5)))
+    ctx.build()
+    blas, _ = ctx.build_stages()
+    assert blas["sort"] > 0.
+    rng = np.random.default_rng(11)
+    n = 3000
+    # rays from outside towards the sphere, and rays from inside
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    ori = np.where(np.arange(n)[:, None] < n // 2, -3. * d / np.linalg.norm(d, axis=1, keepdims=True) + .3 * rng.normal(size=(n, 3)), .2 * rng.normal(size=(n, 3))).astype(np.float32)
+    a_id, a_t = ctx.trace_rays(ori, d, brute=False)
+    b_id, b_t = ctx.trace_rays(ori, d, brute=True)
+    assert np.array_equal(a_id, b_id)
+    assert np.array_equal(a_t, b_t)
+    assert (a_id >= 0).mean() > 0.9
+    # every triangle is reachable through the hierarchy: a ray at each of 5000 random triangles' centroids
+    # from just outside finds that triangle (or, at shared edges, a neighbour at the same distance)
+    pick = rng.integers(0, len(idx), 5000)
+    cen = xyz[idx[pick]].mean(axis=1)
+    o2 = (cen * 1.5).astype(np.float32)
+    d2 = (-cen).astype(np.float32)
+    c_id, c_t = ctx.trace_rays(o2, d2, brute=False)
+    e_id, e_t = ctx.trace_rays(o2, d2, brute=True)
+    assert np.array_equal(c_id, e_id) and np.array_equal(c_t, e_t)
+    assert (c_id >= 0).all()
+    assert (((c_id & 0xffffffff) - 1) == pick).mean() > 0.99               # (ids carry the primitive index + 1)
+    ctx.close()
+
+
 def test_frame_equals_float_mirror_on_the_benchmarked_scene(spheres):
     """A reduced frame of the benchmarked scene (reference mesh mix, 8.8 M instanced triangles,
     depth 50, defocus on) through the render kernel: fixed-point radiance sums and segment counts
