@@ -297,7 +297,7 @@ void lbvh_build( rtx_ctx* c, Lbvh& b, const q4* plo, const q4* phi, uint32_t n, 
 	c->launches += 2 ;
 	for ( int pass = 0 ; pass<8 ; pass++ ) {
 		CK( cudaMemsetAsync( os_status, 0, sizeof( uint32_t )*size_t( 256 )*ntiles, c->stream ) ) ;
-		k_radix_onesweep<<<ntiles, RTX_OS_THREADS, 0, c->stream>>>( kin, vin, n, 8*pass, os_hist+256*pass, os_status, os_hist+8*256+pass, kout, vout ) ;
+		k_radix_onesweep<<<ntiles, RTX_OS_THREADS, RTX_OS_SMEM_BYTES, c->stream>>>( kin, vin, n, 8*pass, os_hist+256*pass, os_status, os_hist+8*256+pass, kout, vout ) ;
 		c->launches += 1 ;
 		std::swap( kin, kout ) ; std::swap( vin, vout ) ;
 	}
@@ -708,6 +708,7 @@ int rtx_init( int device, rtx_ctx** out ) {
 				( const void* ) k_radix_scatter, ( const void* ) k_karras, ( const void* ) k_refit, ( const void* ) k_wide_level, ( const void* ) k_wide_all, ( const void* ) k_scan_chunks, ( const void* ) k_scan_add, ( const void* ) k_pack_tris,
 				( const void* ) k_radix_hist8, ( const void* ) k_radix_bases, ( const void* ) k_radix_onesweep } ;
 			for ( const void* k : kernels ) CK( cudaFuncGetAttributes( &fa, k ) ) ;
+			CK( cudaFuncSetAttribute( k_radix_onesweep, cudaFuncAttributeMaxDynamicSharedMemorySize, int( RTX_OS_SMEM_BYTES ) ) ) ;
 		}
 		// the render kernel is persistent: one warp per CTA, as many CTAs as fit
 		// shared memory holds the ray slots, L1 caches the BVH: the carveout decides how many

@@ -92,6 +92,16 @@ RTX_HD void pad_box( f3& lo, f3& hi ) {
 // box area, as long as that slot is an inner node covering more than leaf_max primitives.
 // Slots: >= 0 binary inner node, < 0 binary leaf slot ~s.  Binary boxes: [0,n-1) inner,
 // [n-1,2n-1) leaves.  (Inner node i covers the sorted range child-range[i].)
+// a 16-byte record of a builder array with one 128-bit load (the arrays are 256-byte aligned pool allocations; q4
+// itself only promises 4-byte alignment, so plain member accesses compile to scalar loads)
+RTX_HD q4 ldbox( const q4* p ) {
+#if defined( __CUDA_ARCH__ )
+	const float4 v = *reinterpret_cast<const float4*>( p ) ;
+	q4 r ; r.x = v.x ; r.y = v.y ; r.z = v.z ; r.w = v.w ; return r ;
+#else
+	return *p ;
+#endif
+}
 RTX_HD float box_area( const q4& lo, const q4& hi ) {
 	const float dx = hi.x-lo.x, dy = hi.y-lo.y, dz = hi.z-lo.z ;
 	return dx*dy+dy*dz+dz*dx ;
@@ -106,7 +116,7 @@ RTX_HD int wide_gather( int bin, const I2* child, const I2* range, const q4* blo
 			const int s = slots[k] ;
 			if ( s<0 || range[s].y-range[s].x+1<=leaf_max )
 				continue ;
-			const float a = box_area( blo[s], bhi[s] ) ;
+			const float a = box_area( ldbox( blo+s ), ldbox( bhi+s ) ) ;
 			if ( a>amax ) { amax = a ; pick = k ; }
 		}
 		if ( pick<0 )
@@ -298,10 +308,13 @@ __global__ void __launch_bounds__( 32*RTX_RS_WARPS ) k_radix_scatter( const uint
 // __match_any_sync (rounds in order, lanes in order: stable), learns where its tile starts in
 // every bucket by looking back over the tiles before it (decoupled look-back: a status word per
 // tile and digit holds the tile's own count first, the inclusive count once it is known; thread d
-// handles digit d), moves keys and values through shared memory into bucket order and writes
-// each bucket's run with consecutive threads on consecutive addresses.
+// handles digit d; the walk comes after the keys and values have been moved into bucket order in
+// shared memory, which needs nothing from other tiles) and writes each bucket's run with
+// consecutive threads on consecutive addresses.
 #define RTX_OS_THREADS 256
+#ifndef RTX_OS_ITEMS
 #define RTX_OS_ITEMS   16
+#endif
 #define RTX_OS_TILE    ( RTX_OS_THREADS*RTX_OS_ITEMS )   // 4096 keys per tile
 #define RTX_OS_WARPS   ( RTX_OS_THREADS/32 )
 #define RTX_OS_AGG     0x40000000u    // status: the tile's own count ...
@@ -359,18 +372,22 @@ __global__ void __launch_bounds__( 256 ) k_radix_bases( uint32_t* hist ) {
 	}
 	row[threadIdx.x] = part[threadIdx.x]-c ;
 }
+// shared memory of a CTA (dynamic: more than the 48 KB a kernel gets without asking)
+#define RTX_OS_SMEM_BYTES ( RTX_OS_TILE*12u+RTX_OS_WARPS*1024u+2u*1024u+64u )
 __global__ void __launch_bounds__( RTX_OS_THREADS, RTX_OS_MIN_CTAS ) k_radix_onesweep( const uint64_t* keys, const uint32_t* vals, uint32_t n, int shift, const uint32_t* bases, uint32_t* status, uint32_t* ticket, uint64_t* keys_out, uint32_t* vals_out ) {
-	__shared__ uint32_t wh[RTX_OS_WARPS][256] ;     // per warp and digit: count, then offset inside the tile's run of the digit
-	__shared__ uint32_t tile_start[256] ;          // first position of the digit's run in the tile's bucket order
-	__shared__ uint32_t gbase[256] ;               // where that run goes in the output
-	__shared__ uint32_t wsum[RTX_OS_WARPS] ;
-	__shared__ uint32_t s_tile ;
-	__shared__ uint64_t stage[RTX_OS_TILE] ;
+	extern __shared__ __align__( 16 ) unsigned char os_smem[] ;
+	uint64_t* stage = reinterpret_cast<uint64_t*>( os_smem ) ;                              // [RTX_OS_TILE] keys in bucket order
+	uint32_t* sval = reinterpret_cast<uint32_t*>( os_smem+RTX_OS_TILE*8u ) ;                // [RTX_OS_TILE] their indices
+	uint32_t ( *wh )[256] = reinterpret_cast<uint32_t ( * )[256]>( os_smem+RTX_OS_TILE*12u ) ;   // per warp and digit: count, then offset inside the tile's run of the digit
+	uint32_t* tile_start = reinterpret_cast<uint32_t*>( os_smem+RTX_OS_TILE*12u+RTX_OS_WARPS*1024u ) ;   // first position of the digit's run in the tile's bucket order
+	uint32_t* gbase = tile_start+256 ;                                                      // where that run goes in the output
+	uint32_t* wsum = gbase+256 ;                                                            // [RTX_OS_WARPS]
+	uint32_t* s_tile = wsum+RTX_OS_WARPS ;
 	const uint32_t tid = threadIdx.x, lane = tid&31u, warp = tid>>5 ;
-	if ( tid == 0 ) s_tile = atomicAdd( ticket, 1u ) ;
+	if ( tid == 0 ) *s_tile = atomicAdd( ticket, 1u ) ;
 	for ( int d = tid ; d<256*RTX_OS_WARPS ; d += RTX_OS_THREADS ) ( &wh[0][0] )[d] = 0 ;
 	__syncthreads() ;
-	const uint32_t tile = s_tile ;
+	const uint32_t tile = *s_tile ;
 	const uint32_t tile0 = tile*RTX_OS_TILE ;
 	const uint32_t base = tile0+warp*( RTX_OS_TILE/RTX_OS_WARPS ) ;
 	uint64_t key[RTX_OS_ITEMS] ;
@@ -382,7 +399,7 @@ __global__ void __launch_bounds__( RTX_OS_THREADS, RTX_OS_MIN_CTAS ) k_radix_one
 		val[r] = i<n ? vals[i] : 0u ;
 	}
 	// ranks inside the warp's run of the tile: the lanes of a round that share a digit find each other
-	// (all rounds' matches first: they are independent), the first of them bumps the warp's counter of
+	// (all rounds first: they are independent), the first of them bumps the warp's counter of
 	// the digit and hands the old value to the others (the atomics of successive rounds queue up in
 	// order -- no round waits for the one before it)
 #pragma unroll
@@ -423,11 +440,11 @@ __global__ void __launch_bounds__( RTX_OS_THREADS, RTX_OS_MIN_CTAS ) k_radix_one
 	uint32_t total = 0 ;
 #pragma unroll
 	for ( int w = 0 ; w<RTX_OS_WARPS ; w++ ) { const uint32_t c = wh[w][tid] ; wh[w][tid] = total ; total += c ; }
-	// publish it, then find out how many keys of this digit the tiles in front hold
+	// publish it for the tiles behind
 	volatile uint32_t* st = status ;
 	if ( tile == 0 ) st[tid] = total|RTX_OS_INCL ;
 	else st[size_t( tile )*256u+tid] = total|RTX_OS_AGG ;
-	// (meanwhile) exclusive scan of the counts over the digits: the tile's bucket order
+	// exclusive scan of the counts over the digits: the tile's bucket order
 	uint32_t incl = total ;
 #pragma unroll
 	for ( int o = 1 ; o<32 ; o <<= 1 ) { const uint32_t v = __shfl_up_sync( 0xffffffffu, incl, o ) ; if ( lane>=uint32_t( o ) ) incl += v ; }
@@ -437,11 +454,22 @@ __global__ void __launch_bounds__( RTX_OS_THREADS, RTX_OS_MIN_CTAS ) k_radix_one
 #pragma unroll
 	for ( int w = 0 ; w<RTX_OS_WARPS ; w++ ) if ( uint32_t( w )<warp ) before += wsum[w] ;
 	tile_start[tid] = before+incl-total ;
+	__syncthreads() ;
+	// keys and indices into bucket order (shared memory) -- this needs nothing from the tiles in front, whose counts
+	// have time to arrive meanwhile
+#pragma unroll
+	for ( int r = 0 ; r<RTX_OS_ITEMS ; r++ )
+		if ( base+uint32_t( r )*32u+lane<n ) {
+			const uint32_t d = uint32_t( key[r]>>shift )&255u ;
+			const uint32_t q = pos[r]+tile_start[d]+wh[warp][d] ;
+			stage[q] = key[r] ;
+			sval[q] = val[r] ;
+		}
+	// how many keys of digit tid the tiles in front hold: walk back, RTX_OS_WINDOW status words per round trip
+	// (independent loads), adding own counts until a tile with an inclusive count turns up (tile 0 publishes
+	// one: the walk ends there at the latest); a word that is not published yet ends the round, the next one starts there
 	uint32_t front = 0 ;
 	if ( tile>0 ) {
-		// walk back over the tiles in front, RTX_OS_WINDOW status words per round trip (independent loads), adding own
-		// counts until a tile with an inclusive count turns up (tile 0 publishes one: the walk ends there at the latest);
-		// a word that is not published yet ends the round, the next one starts there
 		int look = int( tile )-1 ;
 		bool found = false ;
 		while ( ! found ) {
@@ -463,38 +491,18 @@ __global__ void __launch_bounds__( RTX_OS_THREADS, RTX_OS_MIN_CTAS ) k_radix_one
 	}
 	gbase[tid] = bases[tid]+front ;
 	__syncthreads() ;
-	// keys into bucket order, out in runs
-#pragma unroll
-	for ( int r = 0 ; r<RTX_OS_ITEMS ; r++ )
-		if ( base+uint32_t( r )*32u+lane<n ) {
-			const uint32_t d = uint32_t( key[r]>>shift )&255u ;
-			pos[r] += tile_start[d]+wh[warp][d] ;
-			stage[pos[r]] = key[r] ;
-		}
-	__syncthreads() ;
+	// out in runs: consecutive threads write consecutive elements of a bucket
 	const uint32_t n_tile = min( uint32_t( RTX_OS_TILE ), n-tile0 ) ;
-	uint32_t dst[RTX_OS_ITEMS] ;
 #pragma unroll
 	for ( int k = 0 ; k<RTX_OS_ITEMS ; k++ ) {
 		const uint32_t i = uint32_t( k )*RTX_OS_THREADS+tid ;
-		dst[k] = 0 ;
 		if ( i<n_tile ) {
 			const uint64_t kk = stage[i] ;
 			const uint32_t d = uint32_t( kk>>shift )&255u ;
-			dst[k] = gbase[d]+( i-tile_start[d] ) ;
-			keys_out[dst[k]] = kk ;
+			const uint32_t dst = gbase[d]+( i-tile_start[d] ) ;
+			keys_out[dst] = kk ;
+			vals_out[dst] = sval[i] ;
 		}
-	}
-	__syncthreads() ;
-	uint32_t* sv = reinterpret_cast<uint32_t*>( stage ) ;
-#pragma unroll
-	for ( int r = 0 ; r<RTX_OS_ITEMS ; r++ )
-		if ( base+uint32_t( r )*32u+lane<n ) sv[pos[r]] = val[r] ;
-	__syncthreads() ;
-#pragma unroll
-	for ( int k = 0 ; k<RTX_OS_ITEMS ; k++ ) {
-		const uint32_t i = uint32_t( k )*RTX_OS_THREADS+tid ;
-		if ( i<n_tile ) vals_out[dst[k]] = sv[i] ;
 	}
 }
 
@@ -517,25 +525,30 @@ __global__ void __launch_bounds__( 256 ) k_refit( const q4* plo, const q4* phi, 
 	const int j = blockIdx.x*blockDim.x+threadIdx.x ;
 	if ( j>=n ) return ;
 	const uint32_t prim = vals[j] ;
-	f3 lo = mk3( plo[prim].x, plo[prim].y, plo[prim].z ), hi = mk3( phi[prim].x, phi[prim].y, phi[prim].z ) ;
+	const float4 pl = __ldg( reinterpret_cast<const float4*>( plo+prim ) ), ph = __ldg( reinterpret_cast<const float4*>( phi+prim ) ) ;
+	f3 lo = mk3( pl.x, pl.y, pl.z ), hi = mk3( ph.x, ph.y, ph.z ) ;
 	pad_box( lo, hi ) ;
 	q4 qlo = { lo.x, lo.y, lo.z, 0.f }, qhi = { hi.x, hi.y, hi.z, 0.f } ;
-	blo[n-1+j] = qlo ; bhi[n-1+j] = qhi ;
+	*reinterpret_cast<float4*>( blo+( n-1+j ) ) = make_float4( qlo.x, qlo.y, qlo.z, 0.f ) ;
+	*reinterpret_cast<float4*>( bhi+( n-1+j ) ) = make_float4( qhi.x, qhi.y, qhi.z, 0.f ) ;
 	if ( n == 1 ) return ;
 	int p = parent_leaf[j] ;
+	int me = n-1+j ;                       // the node whose box (qlo, qhi) this thread carries upward
 	while ( p>=0 ) {
 		__threadfence() ;
 		if ( atomicAdd( flags+p, 1u ) == 0u )
 			return ;                       // the sibling subtree is not finished: its thread carries on
+		// the second to arrive: own box from registers, the sibling's with two 128-bit loads from L2
+		// (ld.global.cg: written by another thread, in front of its fence and its arrival)
 		const int2 c = child[p] ;
 		const int a = c.x<0 ? n-1+( ~c.x ) : c.x, b = c.y<0 ? n-1+( ~c.y ) : c.y ;
-		const volatile float* alo = reinterpret_cast<const volatile float*>( blo+a ) ;
-		const volatile float* ahi = reinterpret_cast<const volatile float*>( bhi+a ) ;
-		const volatile float* clo = reinterpret_cast<const volatile float*>( blo+b ) ;
-		const volatile float* chi = reinterpret_cast<const volatile float*>( bhi+b ) ;
-		q4 nlo = { fminf( alo[0], clo[0] ), fminf( alo[1], clo[1] ), fminf( alo[2], clo[2] ), 0.f } ;
-		q4 nhi = { fmaxf( ahi[0], chi[0] ), fmaxf( ahi[1], chi[1] ), fmaxf( ahi[2], chi[2] ), 0.f } ;
-		blo[p] = nlo ; bhi[p] = nhi ;
+		const int sib = a == me ? b : a ;
+		const float4 slo = __ldcg( reinterpret_cast<const float4*>( blo+sib ) ), shi = __ldcg( reinterpret_cast<const float4*>( bhi+sib ) ) ;
+		qlo = { fminf( qlo.x, slo.x ), fminf( qlo.y, slo.y ), fminf( qlo.z, slo.z ), 0.f } ;
+		qhi = { fmaxf( qhi.x, shi.x ), fmaxf( qhi.y, shi.y ), fmaxf( qhi.z, shi.z ), 0.f } ;
+		*reinterpret_cast<float4*>( blo+p ) = make_float4( qlo.x, qlo.y, qlo.z, 0.f ) ;   // (one 128-bit store each: q4 itself only promises 4-byte alignment)
+		*reinterpret_cast<float4*>( bhi+p ) = make_float4( qhi.x, qhi.y, qhi.z, 0.f ) ;
+		me = p ;
 		p = parent_inner[p] ;
 	}
 }
@@ -555,7 +568,8 @@ __device__ __forceinline__ void wide_item( const int2 item, int n, int leaf_max,
 		for ( int k = 0 ; k<ns ; k++ ) {
 			const int s = slots[k] ;
 			const int b = s<0 ? n-1+( ~s ) : s ;
-			lo[0][k] = blo[b].x ; lo[1][k] = blo[b].y ; lo[2][k] = blo[b].z ; hi[0][k] = bhi[b].x ; hi[1][k] = bhi[b].y ; hi[2][k] = bhi[b].z ;
+			const q4 bl = ldbox( blo+b ), bh = ldbox( bhi+b ) ;
+			lo[0][k] = bl.x ; lo[1][k] = bl.y ; lo[2][k] = bl.z ; hi[0][k] = bh.x ; hi[1][k] = bh.y ; hi[2][k] = bh.z ;
 			if ( ! wide_leaf_ref( s, range, leaf_max, ref[k] ) ) {
 				const uint32_t idx = atomicAdd( counters, 1u ) ;
 				next[atomicAdd( counters+1, 1u )] = make_int2( s, int( idx ) ) ;
@@ -567,11 +581,12 @@ __device__ __forceinline__ void wide_item( const int2 item, int n, int leaf_max,
 		q4* o = nodes+size_t( item.y )*RTX_NODE_RECS+8*h ;
 		for ( int a = 0 ; a<3 ; a++ ) {
 			for ( int k = 4*h ; k<4*h+4 ; k++ ) box_ch( lo[a][k], hi[a][k], lo[a][k], hi[a][k] ) ;   // (centre / half extent for 4-wide nodes)
-			o[a]   = { lo[a][4*h], lo[a][4*h+1], lo[a][4*h+2], lo[a][4*h+3] } ;
-			o[3+a] = { hi[a][4*h], hi[a][4*h+1], hi[a][4*h+2], hi[a][4*h+3] } ;
+			// (128-bit stores: the node array is 128-byte aligned)
+			reinterpret_cast<float4*>( o )[a]   = make_float4( lo[a][4*h], lo[a][4*h+1], lo[a][4*h+2], lo[a][4*h+3] ) ;
+			reinterpret_cast<float4*>( o )[3+a] = make_float4( hi[a][4*h], hi[a][4*h+1], hi[a][4*h+2], hi[a][4*h+3] ) ;
 		}
-		o[6] = { __int_as_float( ref[4*h] ), __int_as_float( ref[4*h+1] ), __int_as_float( ref[4*h+2] ), __int_as_float( ref[4*h+3] ) } ;
-		o[7] = { 0.f, 0.f, 0.f, 0.f } ;
+		reinterpret_cast<float4*>( o )[6] = make_float4( __int_as_float( ref[4*h] ), __int_as_float( ref[4*h+1] ), __int_as_float( ref[4*h+2] ), __int_as_float( ref[4*h+3] ) ) ;
+		reinterpret_cast<float4*>( o )[7] = make_float4( 0.f, 0.f, 0.f, 0.f ) ;
 	}
 }
 __global__ void __launch_bounds__( 128 ) k_wide_level( const int2* frontier, uint32_t n_front, int n, int leaf_max, const int2* child, const int2* range, const q4* blo, const q4* bhi, q4* nodes, int2* next, uint32_t* counters ) {
