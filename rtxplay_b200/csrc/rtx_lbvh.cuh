@@ -621,8 +621,8 @@ __global__ void __launch_bounds__( 256 ) k_tri_bounds( const float* vces, const 
 	if ( f>=nt ) return ;
 	const uint32_t i0 = ices[3*size_t( f )], i1 = ices[3*size_t( f )+1], i2 = ices[3*size_t( f )+2] ;
 	const float* a = vces+3*size_t( i0 ) ; const float* b = vces+3*size_t( i1 ) ; const float* c = vces+3*size_t( i2 ) ;
-	plo[f] = { fminf( a[0], fminf( b[0], c[0] ) ), fminf( a[1], fminf( b[1], c[1] ) ), fminf( a[2], fminf( b[2], c[2] ) ), 0.f } ;
-	phi[f] = { fmaxf( a[0], fmaxf( b[0], c[0] ) ), fmaxf( a[1], fmaxf( b[1], c[1] ) ), fmaxf( a[2], fmaxf( b[2], c[2] ) ), 0.f } ;
+	*reinterpret_cast<float4*>( plo+f ) = make_float4( fminf( a[0], fminf( b[0], c[0] ) ), fminf( a[1], fminf( b[1], c[1] ) ), fminf( a[2], fminf( b[2], c[2] ) ), 0.f ) ;
+	*reinterpret_cast<float4*>( phi+f ) = make_float4( fmaxf( a[0], fmaxf( b[0], c[0] ) ), fmaxf( a[1], fmaxf( b[1], c[1] ) ), fmaxf( a[2], fmaxf( b[2], c[2] ) ), 0.f ) ;
 }
 // triangles in leaf order: (a, prim) (e1, b.x) (e2, b.y) (b.z, c) -- the edges are float differences (contract)
 __global__ void __launch_bounds__( 256 ) k_pack_tris( const float* vces, const uint32_t* ices, const uint32_t* vals, uint32_t nt, q4* tris ) {
@@ -631,11 +631,12 @@ __global__ void __launch_bounds__( 256 ) k_pack_tris( const float* vces, const u
 	const uint32_t f = vals[j] ;
 	const uint32_t i0 = ices[3*size_t( f )], i1 = ices[3*size_t( f )+1], i2 = ices[3*size_t( f )+2] ;
 	const float* a = vces+3*size_t( i0 ) ; const float* b = vces+3*size_t( i1 ) ; const float* c = vces+3*size_t( i2 ) ;
-	q4* T = tris+size_t( j )*RTX_TRI_RECS ;
-	T[0] = { a[0], a[1], a[2], __int_as_float( int( f ) ) } ;
-	T[1] = { b[0]-a[0], b[1]-a[1], b[2]-a[2], b[0] } ;
-	T[2] = { c[0]-a[0], c[1]-a[1], c[2]-a[2], b[1] } ;
-	T[3] = { b[2], c[0], c[1], c[2] } ;   // the vertices as uploaded, for the shading frame
+	float4* T = reinterpret_cast<float4*>( tris+size_t( j )*RTX_TRI_RECS ) ;   // (128-bit stores: the record array is 64-byte aligned)
+	const float ax = a[0], ay = a[1], az = a[2], bx = b[0], by = b[1], bz = b[2], cx = c[0], cy = c[1], cz = c[2] ;
+	T[0] = make_float4( ax, ay, az, __int_as_float( int( f ) ) ) ;
+	T[1] = make_float4( bx-ax, by-ay, bz-az, bx ) ;
+	T[2] = make_float4( cx-ax, cy-ay, cz-az, by ) ;
+	T[3] = make_float4( bz, cx, cy, cz ) ;   // the vertices as uploaded, for the shading frame
 }
 // world bounds of every thing: analytic sphere c +- r; mesh = its root box corners mapped
 // through the double transform.  root boxes are [lo,hi] of each thing's mesh.
