@@ -97,6 +97,11 @@ __device__ __forceinline__ void red_add_u64( unsigned long long* addr, unsigned 
 #ifndef RTX_NODE_BIAS
 #define RTX_NODE_BIAS 0         // votes added to the node kind
 #endif
+#ifndef RTX_LONE
+#define RTX_LONE 0             // (experiment) lanes left in a warp below which the tail of a launch runs without votes.  Measured with 2 / 4:
+                              // the 500-spp frame 594.0 / 594.3 against 581.8 ms (the second copy of the step functions costs the main loop 2 %),
+                              // the 63-spp frame 79.4 / 79.3 against 77.4, the 1-spp frame 5.4 / 5.2 against 5.1 ms: the votes are not what the tail waits for
+#endif
 #ifndef RTX_UNIT_SPP
 #define RTX_UNIT_SPP 64u        // samples per pixel of a full work unit (16-128 measured alike; swept with the taper in place)
 #endif
@@ -143,6 +148,33 @@ inline void unit_plan( FrameArgs& a ) {
 	}
 	a.taper_s0[n] = uint16_t( s ) ;
 	a.chunks_taper = n ;
+}
+// SHADE step of one lane + what it adds to the frame: the guide sums of a first diffuse / reflecting hit, and
+// the radiance and segment count of a path that has ended
+template <bool GUIDES, class P>
+__device__ __forceinline__ int shade_and_accumulate( P& p, int slot, const SceneDev& S, unsigned long long* accum, unsigned long long* guide ) {
+	f3 c, gn, ga ; bool g ;
+	uint32_t segments ;
+	const int nk = step_shade( p, slot, S, c, g, gn, ga, segments ) ;
+	const size_t pix = size_t( uint32_t( p.i( F_PIX, slot ) ) ) ;
+	if ( GUIDES && g ) {
+		const float v[6] = { gn.x, gn.y, gn.z, ga.x, ga.y, ga.z } ;
+		for ( int q = 0 ; q<6 ; q++ )
+			red_add_u64( guide+6*pix+q, ( unsigned long long )( long long )( v[q]*1073741824.f ) ) ;
+	}
+	if ( nk == K_REGEN ) {
+		// (0 contributions -- absorbed paths -- need no atomic)
+		const unsigned long long r = tofix( c.x ), gg = tofix( c.y ), bb = tofix( c.z ) ;
+#if ! defined( RTX_EXPERIMENT_NO_ACCUM )
+		if ( r )  red_add_u64( accum+4*pix, r ) ;
+		if ( gg ) red_add_u64( accum+4*pix+1, gg ) ;
+		if ( bb ) red_add_u64( accum+4*pix+2, bb ) ;
+		red_add_u64( accum+4*pix+3, ( unsigned long long ) segments ) ;
+#else
+		if ( r+gg+bb == 1 ) atomicAdd( accum+4*pix+3, ( unsigned long long ) segments ) ;
+#endif
+	}
+	return nk ;
 }
 #if defined( RTX_MAXNREG )
 #define RTX_RENDER_BOUNDS __maxnreg__( RTX_MAXNREG )                 // (tuning: an exact register budget instead of a CTA count)
@@ -197,6 +229,22 @@ __global__ void RTX_RENDER_BOUNDS k_render( const __grid_constant__ FrameArgs a,
 #endif
 
 	while ( true ) {
+#if RTX_LONE && RTX_K == 1 && ! defined( RTX_DEVICE_COUNTERS )
+		// the end of a launch: no paths left to hand out and at most RTX_LONE lanes of the warp still on a path (the few that
+		// bounce dozens of times inside a glass sphere).  There is nothing to schedule any more: each lane runs its path to
+		// the end on its own, one step after the other, without the vote and the dispatch of every iteration
+		if ( exhausted && __popc( __ballot_sync( 0xffffffffu, kinds[0] != K_DONE ) )<=RTX_LONE ) {
+			int k = kinds[0] ;
+			while ( k != K_DONE ) {
+				if ( k == K_NODE ) k = step_node( p, int( lane ), a.S ) ;
+				else if ( k == K_LEAF ) k = step_leaf( p, int( lane ), a.S ) ;
+				else if ( k == K_THING ) k = step_thing( p, int( lane ), a.S ) ;
+				else if ( k == K_SHADE ) k = shade_and_accumulate<GUIDES>( p, int( lane ), a.S, accum, guide ) ;
+				else k = K_DONE ;   // (a new path: there is none)
+			}
+			break ;
+		}
+#endif
 		// vote: which step kind can most lanes take?
 #if RTX_K == 1
 		// one ray per lane: lanes of equal kind find each other (match), the largest group
@@ -261,29 +309,7 @@ __global__ void RTX_RENDER_BOUNDS k_render( const __grid_constant__ FrameArgs a,
 				break ;
 			case K_SHADE:
 				RTX_COUNT_STEP( K_SHADE, __ballot_sync( 0xffffffffu, j>=0 ) ) ;
-				if ( j>=0 ) {
-					f3 c, gn, ga ; bool g ;
-					uint32_t segments ;
-					nk = step_shade( p, slot, a.S, c, g, gn, ga, segments ) ;
-					const size_t pix = size_t( uint32_t( p.i( F_PIX, slot ) ) ) ;
-					if ( GUIDES && g ) {
-						const float v[6] = { gn.x, gn.y, gn.z, ga.x, ga.y, ga.z } ;
-						for ( int q = 0 ; q<6 ; q++ )
-							red_add_u64( guide+6*pix+q, ( unsigned long long )( long long )( v[q]*1073741824.f ) ) ;
-					}
-					if ( nk == K_REGEN ) {
-						// (0 contributions -- absorbed paths -- need no atomic)
-						const unsigned long long r = tofix( c.x ), gg = tofix( c.y ), bb = tofix( c.z ) ;
-#if ! defined( RTX_EXPERIMENT_NO_ACCUM )
-						if ( r )  red_add_u64( accum+4*pix, r ) ;
-						if ( gg ) red_add_u64( accum+4*pix+1, gg ) ;
-						if ( bb ) red_add_u64( accum+4*pix+2, bb ) ;
-						red_add_u64( accum+4*pix+3, ( unsigned long long ) segments ) ;
-#else
-						if ( r+gg+bb == 1 ) atomicAdd( accum+4*pix+3, ( unsigned long long ) segments ) ;
-#endif
-					}
-				}
+				if ( j>=0 ) nk = shade_and_accumulate<GUIDES>( p, slot, a.S, accum, guide ) ;
 				break ;
 			default: {   // K_REGEN: hand the next paths of the warp's unit(s) to the lanes that ask
 				uint32_t want = __ballot_sync( 0xffffffffu, j>=0 ) ;
