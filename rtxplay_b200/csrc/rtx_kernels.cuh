@@ -88,11 +88,12 @@ __device__ __forceinline__ void red_add_u64( unsigned long long* addr, unsigned 
 // integer atomics: order free, bit-reproducible, and no per-tile buffers.
 #define RTX_POOL_R ( 32*RTX_K )
 #ifndef RTX_STICKY
-#define RTX_STICKY 5           // keep doing node steps while at least this many lanes have one (4: 586.7, 5: 582.9, 6: 580.8, 8: 581.3 ms per frame)
+#define RTX_STICKY 6           // keep doing node steps while at least this many lanes have one (launch bound 18: 4 / 5 / 6 / 8 -> 586.7 / 582.9 / 580.8 / 581.3 ms per frame; launch bound 17: 4 / 5 / 6 / 7 / 8 -> 578.4 / 573.7 / 571.7 / 571.4 / 571.5)
 #endif
 #ifndef RTX_MIN_CTAS
-#define RTX_MIN_CTAS 18         // launch bound: 17-20 all compile to 96 registers = 5 warps per scheduler, 20 per SM (24 at 80
-                                // registers measure 9 % slower); 18/19 happen to schedule the code 4 % better than 20
+#define RTX_MIN_CTAS 17         // launch bound: 17-20 all compile to 96 registers = 5 warps per scheduler, 20 per SM (24 at 80
+                                // registers measure 9 % slower); which of them schedules the code best changes with the code --
+                                // 17 / 18 / 19 / 20: 574.2 / 582.3 / 582.2 / 586.4 ms per frame with the final step functions
 #endif
 #ifndef RTX_NODE_BIAS
 #define RTX_NODE_BIAS 0         // votes added to the node kind
